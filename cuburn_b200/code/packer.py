@@ -1,0 +1,195 @@
+"""
+Genome packing: which knot rows go to the device, which parameter slots the
+iterate kernel reads, and the precalc program that connects them.
+
+Plays the role of the reference ``GenomePacker`` (cuburn/code/interp.py:125-282)
+with a different mechanism.  The reference discovers the required splines as a
+side effect of rendering code templates and emits a C struct plus a generated
+interpolation kernel.  Here the genome *structure* (which xforms, variations,
+post-affines and final xform exist) is walked once and turned into data:
+
+  rows     unique spline paths -> rows of the ``times``/``knots`` [nrows][32]
+           upload (pack(), same content as interp.py:207-232)
+  slots    named floats of one temporal sample's parameter block
+  program  int32 [nops][12] precalc ops interpreted by the static kernel
+           ``cb_interp_params`` (csrc/cb_interp.cu)
+
+Slot and row names are dotted genome paths, so a CPU restatement can be compared
+by name without knowing the layout.
+"""
+import numpy as np
+
+from ..genome import specs
+from ..genome.use import SplineEval
+from ..genome.util import resolve_spec
+from ..genome.variations import var_param_order
+from . import varlib
+from .varlib import (OP_DIRECT, OP_DIRECT_MAG, OP_AFFINE, OP_CAMERA, OP_DENSITY)
+
+SEARCH_ROUNDS = 5
+MAX_KNOTS = 1 << SEARCH_ROUNDS
+PROG_WIDTH = 12
+AFFINE_COEFS = ('xx', 'xy', 'xo', 'yx', 'yy', 'yo')
+_AFFINE_INPUTS = (('angle',), ('spread',), ('magnitude', 'x'), ('magnitude', 'y'),
+                  ('offset', 'x'), ('offset', 'y'))
+
+
+class GenomePacker(object):
+    def __init__(self, gnm, spec=None):
+        self.spec = spec or specs.anim
+        self.row_paths = []          # tuple paths
+        self.row_mag = []            # 1 for magnitude-domain rows
+        self._row_index = {}
+        self.slot_names = []         # dotted names
+        self._slot_index = {}
+        self.program = []            # lists of PROG_WIDTH ints
+
+        # xform order = string sort of the keys; the last one takes the
+        # remainder of the probability mass (iter.py:232,263-272)
+        self.xform_ids = sorted(str(k) for k in gnm.get('xforms', {}).keys())
+        if not self.xform_ids:
+            raise ValueError('genome has no xforms')
+        self.has_final = 'final_xform' in gnm
+        # (xform path, variation names in sorted order, has post affine)
+        self.xforms = []
+
+        # weights first so the density op sees one contiguous block of rows
+        wrows = [self._row(('xforms', xid, 'weight')) for xid in self.xform_ids]
+        assert wrows == list(range(len(wrows)))
+
+        for xid in self.xform_ids:
+            self._add_xform(('xforms', xid), gnm['xforms'][xid])
+        if self.has_final:
+            self._add_xform(('final_xform',), gnm['final_xform'])
+
+        if len(self.xform_ids) > 1:
+            first = None
+            for xid in self.xform_ids[:-1]:
+                s = self._slot(('xforms', xid, 'density'))
+                first = s if first is None else first
+            self._op(OP_DENSITY, first, [wrows[0]], aux0=len(self.xform_ids))
+
+        cam_rows = [self._row(('camera', 'rotation')),
+                    self._row(('camera', 'center', 'x')),
+                    self._row(('camera', 'center', 'y')),
+                    self._row(('camera', 'scale'))]
+        cam_first = self._slot_block(('camera',), AFFINE_COEFS)
+        self._op(OP_CAMERA, cam_first, cam_rows)
+
+        self.nrows = len(self.row_paths)
+        self.nslots = len(self.slot_names)
+        # parameter block stride: padded to 16 B so blocks stay vector-aligned
+        self.param_stride = (self.nslots + 3) // 4 * 4
+
+    # ---- structure walk ------------------------------------------------------
+    def _add_xform(self, xpath, xf):
+        variations = sorted(xf.get('variations', {}).keys())
+        for v in variations:
+            if v not in var_param_order:
+                raise KeyError('unknown variation %r' % v)
+        has_post = 'post_affine' in xf
+        self.xforms.append((xpath, variations, has_post))
+
+        self._affine(xpath + ('pre_affine',))
+        if has_post:
+            self._affine(xpath + ('post_affine',))
+        self._direct(xpath + ('color',))
+        self._direct(xpath + ('color_speed',))
+        for v in variations:
+            vpath = xpath + ('variations', v)
+            self._direct(vpath + ('weight',))
+            for kind, name in varlib.var_args(v):
+                if kind == 'p':
+                    self._direct(vpath + (name,))
+            if v in varlib.PRECALC:
+                op, inputs, outputs = varlib.PRECALC[v]
+                rows = []
+                for inp in inputs:
+                    if inp.startswith('^'):
+                        rows.append(self._row(xpath + tuple(inp[1:].split('.'))))
+                    else:
+                        rows.append(self._row(vpath + (inp,)))
+                first = self._slot_block(vpath, outputs)
+                self._op(op, first, rows)
+
+    def _affine(self, apath):
+        rows = [self._row(apath + sub) for sub in _AFFINE_INPUTS]
+        first = self._slot_block(apath, AFFINE_COEFS)
+        self._op(OP_AFFINE, first, rows)
+
+    def _direct(self, path):
+        row = self._row(path)
+        slot = self._slot(path)
+        self._op(OP_DIRECT_MAG if self.row_mag[row] else OP_DIRECT, slot, [row])
+
+    # ---- tables ----------------------------------------------------------------
+    def _row(self, path):
+        if path not in self._row_index:
+            sp = resolve_spec(self.spec, path)
+            self._row_index[path] = len(self.row_paths)
+            self.row_paths.append(path)
+            self.row_mag.append(1 if sp.interp == 'mag' else 0)
+        return self._row_index[path]
+
+    def _slot(self, path):
+        name = '.'.join(path)
+        if name in self._slot_index:
+            raise AssertionError('slot %s allocated twice' % name)
+        self._slot_index[name] = len(self.slot_names)
+        self.slot_names.append(name)
+        return self._slot_index[name]
+
+    def _slot_block(self, path, names):
+        first = None
+        for n in names:
+            s = self._slot(path + (n,))
+            first = s if first is None else first
+        return first
+
+    def _op(self, op, out, rows, aux0=0, aux1=0):
+        assert len(rows) <= 8
+        word = [op, out] + list(rows) + [0] * (8 - len(rows)) + [aux0, aux1]
+        self.program.append(word)
+
+    def slot(self, *path):
+        """Index of a parameter slot by path, e.g. slot('camera', 'xx')."""
+        if len(path) == 1 and isinstance(path[0], (tuple, list)):
+            path = tuple(path[0])
+        return self._slot_index['.'.join(path)]
+
+    def __len__(self):
+        return self.nslots
+
+    # ---- data ------------------------------------------------------------------
+    def program_array(self):
+        return np.asarray(self.program, dtype=np.int32).reshape(-1, PROG_WIDTH)
+
+    def pack(self, gnm, times=None, knots=None):
+        """
+        Knot times and values for every row: two float32 [nrows][32] arrays
+        (times padded with 1e9).  Missing genome keys take the schema default
+        (interp.py:207-232).  ``times`` / ``knots`` may be preallocated (pinned)
+        arrays to fill in place.
+        """
+        if times is None:
+            times = np.empty((self.nrows, MAX_KNOTS), np.float32)
+        if knots is None:
+            knots = np.empty((self.nrows, MAX_KNOTS), np.float32)
+        times.fill(1e9)
+        knots.fill(0)
+        scale = gnm.get('time', {}).get('duration', 1)
+        for idx, path in enumerate(self.row_paths):
+            attr = gnm
+            for name in path:
+                if not isinstance(attr, dict) or name not in attr:
+                    attr = resolve_spec(self.spec, path).default
+                    break
+                attr = attr[name]
+            kn = SplineEval.normalize(attr, scale)
+            n = kn.shape[1]
+            if n > MAX_KNOTS:
+                raise ValueError('%s has %d knots; at most %d are supported'
+                                 % ('.'.join(path), n, MAX_KNOTS))
+            times[idx, :n] = kn[0]
+            knots[idx, :n] = kn[1]
+        return times, knots

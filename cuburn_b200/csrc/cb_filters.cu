@@ -1,0 +1,422 @@
+// The filter chain on the float4 accumulation buffer: YUV->RGB, directional
+// Gaussian blurs, the directional bilateral density-estimation filter,
+// log-scale, and the colorclip / haloclip / smearclip / plainclip / logencode
+// tone-mapping kernels.
+//
+// Semantics follow the reference kernels (cuburn/code/filters.py:4-413,
+// cuburn/code/color.py:12-42); launch recipes live in cuburn_b200/filters.py.
+// The reference samples through 2-D texture references with unnormalised
+// coordinates; CUDA 12 has no texture references, and on B200 plain vector
+// loads through L1/L2 are the natural replacement: neighbours are addressed
+// with clamp-to-edge indices.  This file is compiled with
+// --use_fast_math like the reference's modules (code/util.py:96).
+#include "cb_common.h"
+
+#define K_SQRT2 1.41421353816986f
+
+// 16 filter directions in image addressing ((0,0) upper left, +y down):
+// 0, 90, +-45, +-22.5, 67.5/112.5, +-30, 60/120, +-15, 75/105 degrees
+// (code/filters.py:8-17).
+__constant__ float2 c_dirs[16] = {
+    {1.0f, 0.0f},        {0.0f, 1.0f},
+    {1.0f, 1.0f},        {-1.0f, 1.0f},
+    {1.0f, 0.5f},        {-0.5f, 1.0f},
+    {1.0f, -0.5f},       {0.5f, 1.0f},
+    {1.0f, 0.666667f},   {-0.666667f, 1.0f},
+    {1.0f, -0.666667f},  {0.666667f, 1.0f},
+    {1.0f, 0.333333f},   {-0.333333f, 1.0f},
+    {1.0f, -0.333333f},  {0.333333f, 1.0f},
+};
+
+struct coefs7 { float c[7]; };
+
+// Offset of a tap `radius` steps along direction `pattern`: each component is
+// rounded to nearest-even *before* the pixel position is added, so the tap
+// pattern is identical at every pixel (tex_shear, code/filters.py:22-35).
+__device__ __forceinline__ int2 shear_offset(int pattern, float radius) {
+    float2 d = c_dirs[pattern];
+    return make_int2(__float2int_rn(d.x * radius), __float2int_rn(d.y * radius));
+}
+
+__device__ __forceinline__ int clamp_idx(int x, int y, int w, int h) {
+    x = min(max(x, 0), w - 1);
+    y = min(max(y, 0), h - 1);
+    return y * w + x;
+}
+
+#define PIX_XY()                                                  \
+    int xi = blockIdx.x * 32 + threadIdx.x;                       \
+    int yi = blockIdx.y * 8 + threadIdx.y;                        \
+    int gi = yi * dim.astride + xi
+
+// ---- pointwise kernels: one float4 per thread, exact 1-D grid ---------------
+__global__ void __launch_bounds__(256)
+k_yuv_to_rgb(float4 *dst, const float4 *src) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = src[i];
+    // remove the +0.5 per-sample chroma bias, then JPEG full-range YUV->RGB
+    float u = p.y - 0.5f * p.w, v = p.z - 0.5f * p.w;
+    float r = p.x + 1.402f * v;
+    float g = p.x - 0.34414f * u - 0.71414f * v;
+    float b = p.x + 1.772f * u;
+    dst[i] = make_float4(fmaxf(0.0f, r), fmaxf(0.0f, g), fmaxf(0.0f, b), p.w);
+}
+
+__global__ void __launch_bounds__(256)
+k_logscale(float4 *dst, const float4 *src, float k1, float k2) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = src[i];
+    float ls = fmaxf(0.0f, k1 * logf(1.0f + p.w * k2) / p.w);
+    dst[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+}
+
+__global__ void __launch_bounds__(256)
+k_logencode(float4 *dst, const float4 *src, float degamma) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = src[i];
+    p.x = log2f(powf(p.x, degamma)) / 12.0f + 1.0f;
+    p.y = log2f(powf(p.y, degamma)) / 12.0f + 1.0f;
+    p.z = log2f(powf(p.z, degamma)) / 12.0f + 1.0f;
+    p.w = log2f(powf(p.w, degamma)) / 12.0f + 1.0f;
+    dst[i] = p;
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_gamma(float *dst, const float4 *src, float gamma) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    dst[i] = powf(src[i].x, gamma);
+}
+
+__global__ void __launch_bounds__(256)
+k_haloclip(float4 *pix, const float *den, float gamma_m_1) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = pix[i];
+    float area = den[i];
+    if (p.w <= 0.0f) {
+        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    float ls = powf(p.w, gamma_m_1) / fmaxf(1.0f, area);
+    pix[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_gamma_full_hi(float4 *dst, const float4 *src, float gamma_m_1) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = src[i];
+    float ls = 0.0f;
+    if (p.w > 0.0f) ls = fmaxf(0.0f, p.w - 1.0f) / p.w;
+    dst[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+}
+
+__device__ __forceinline__ float gamma_toe(float w, float gamma_m_1, float linrange,
+                                           float lingam) {
+    float ls = powf(w, gamma_m_1);
+    if (w < linrange) {
+        float frac = w / linrange;
+        ls = (1.0f - frac) * lingam + frac * ls;
+    }
+    return ls;
+}
+
+__global__ void __launch_bounds__(256)
+k_smearclip(float4 *pix, const float4 *smear, float gamma_m_1, float linrange,
+            float lingam) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = pix[i], a = smear[i];
+    p.x += a.x; p.y += a.y; p.z += a.z; p.w += a.w;
+    if (p.w <= 0.0f) {
+        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    float ls = gamma_toe(p.w, gamma_m_1, linrange, lingam);
+    pix[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+}
+
+__global__ void __launch_bounds__(256)
+k_plainclip(float4 *pix, float gamma_m_1, float linrange, float lingam,
+            float brightness) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = pix[i];
+    if (p.w <= 0.0f) {
+        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    float ls = gamma_toe(p.w, gamma_m_1, linrange, lingam) * brightness;
+    pix[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+}
+
+// flam3-style gamma / vibrancy / highlight-power clip (code/filters.py:354-412)
+__global__ void __launch_bounds__(256)
+k_colorclip(float4 *pix, float vibrance, float highpow, float gamma,
+            float linrange, float lingam) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = pix[i];
+    if (p.w <= 0.0f) {
+        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    float4 o = p;
+    float alpha = powf(p.w, gamma);
+    if (p.w < linrange) {
+        float frac = p.w / linrange;
+        alpha = (1.0f - frac) * p.w * lingam + frac * alpha;
+    }
+    float ls = vibrance * alpha / p.w;
+    alpha = fminf(1.0f, fmaxf(0.0f, alpha));
+
+    float maxc = fmaxf(p.x, fmaxf(p.y, p.z));
+    float maxa = maxc * ls;
+    float newls = 1.0f / maxc;
+
+    if (maxa > 1.0f && highpow >= 0.0f) {
+        // desaturate towards white in proportion to the overshoot
+        float lsratio = powf(newls / ls, highpow);
+        p.x = maxc - (maxc - p.x * newls) * lsratio;
+        p.y = maxc - (maxc - p.y * newls) * lsratio;
+        p.z = maxc - (maxc - p.z * newls) * lsratio;
+    } else {
+        float adjhlp = -highpow;
+        if (adjhlp > 1.0f || maxa <= 1.0f) adjhlp = 1.0f;
+        if (maxc > 0.0f) {
+            float adj = (1.0f - adjhlp) * newls + adjhlp * ls;
+            p.x *= adj; p.y *= adj; p.z *= adj;
+        }
+    }
+    float rest = 1.0f - vibrance;
+    p.x += rest * powf(o.x, gamma);
+    p.y += rest * powf(o.y, gamma);
+    p.z += rest * powf(o.z, gamma);
+    pix[i] = make_float4(fminf(1.0f, p.x), fminf(1.0f, p.y), fminf(1.0f, p.z), alpha);
+}
+
+// ---- 7-tap directional blurs ----------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_den_blur(float *dst, const float4 *src, int pattern, int upsample, coefs7 k,
+           cb_dims dim) {
+    PIX_XY();
+    float den = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        int2 o = shear_offset(pattern, (float)((i - 3) * (1 << upsample)));
+        den += src[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].w * k.c[i];
+    }
+    dst[gi] = den;
+}
+
+__global__ void __launch_bounds__(256)
+k_den_blur_1c(float *dst, const float *src, int pattern, int upsample, coefs7 k,
+              cb_dims dim) {
+    PIX_XY();
+    float den = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        int2 o = shear_offset(pattern, (float)((i - 3) * (1 << upsample)));
+        den += src[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)] * k.c[i];
+    }
+    dst[gi] = den;
+}
+
+__global__ void __launch_bounds__(256)
+k_full_blur(float4 *dst, const float4 *src, int pattern, int upsample, coefs7 k,
+            cb_dims dim) {
+    PIX_XY();
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        int2 o = shear_offset(pattern, (float)((i - 3) * (1 << upsample)));
+        float4 p = src[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)];
+        acc.x += p.x * k.c[i];
+        acc.y += p.y * k.c[i];
+        acc.z += p.z * k.c[i];
+        acc.w += p.w * k.c[i];
+    }
+    dst[gi] = acc;
+}
+
+// ---- directional bilateral filter (code/filters.py:166-264) -------------------
+// Weighted mean of the 2*radius+1 taps along one direction.  Weight = spatial
+// term x colour-distance term x density-distance term x (for r != 0) a Gompertz
+// gradient term that pulls energy uphill.
+__global__ void __launch_bounds__(256)
+k_bilateral(float4 *dst, const float4 *src, const float *blur, int pattern,
+            int radius, float sstd, float cstd, float dstd, float dpow,
+            float gspeed, cb_dims dim) {
+    PIX_XY();
+    __shared__ float spa[32];
+    if (threadIdx.y == 0) {
+        float df = (float)threadIdx.x;
+        spa[threadIdx.x] = expf(df * df / (-K_SQRT2 * sstd));
+    }
+    const int W = dim.astride, H = dim.aheight;
+    const float cscale = 1.0f / (-K_SQRT2 * 3.0f * cstd);
+    const float dscale = -0.5f / dstd;
+
+    float4 cen = src[gi];
+    float cdrcp = 1.0f / (cen.w + 1.0e-6f);
+    cen.x *= cdrcp; cen.y *= cdrcp; cen.z *= cdrcp;
+    float cpowden = powf(cen.w, dpow);
+
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float wsum = 0.0f;
+    __syncthreads();
+
+    int2 o = shear_offset(pattern, (float)(-radius - 1));
+    float4 pix = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
+    o = shear_offset(pattern, (float)(-radius));
+    float4 next = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
+
+    for (int r = -radius; r <= radius; r++) {
+        float prev = pix.w;
+        pix = next;
+        o = shear_offset(pattern, (float)(r + 1));
+        next = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
+
+        float cdiff = 0.5f;
+        if (pix.w > 0.0f && cen.w > 0.0f) {
+            float pdrcp = 1.0f / pix.w;
+            float yd = pix.x * pdrcp - cen.x;
+            float ud = pix.y * pdrcp - cen.y;
+            float vd = pix.z * pdrcp - cen.z;
+            cdiff = yd * yd + ud * ud + vd * vd;
+        }
+        float powden = powf(pix.w, dpow);
+        float dfact = exp2f(dscale * fabsf(cpowden - powden));
+
+        o = shear_offset(pattern, (float)r);
+        float avg = blur[clamp_idx(xi + o.x, yi + o.y, W, H)];
+        float grad = (next.w - prev) / (avg + 1.0e-6f);
+        if (r < 0) grad = -grad;
+        float gfact = exp2f(-exp2f(gspeed * grad));
+
+        float f = spa[abs(r)] * expf(cscale * cdiff) * dfact;
+        if (r != 0) f *= gfact;
+        wsum += f;
+        acc.x += f * pix.x;
+        acc.y += f * pix.y;
+        acc.z += f * pix.z;
+        acc.w += f * pix.w;
+    }
+    float rcp = 1.0f / (wsum + 1e-10f);
+    dst[gi] = make_float4(acc.x * rcp, acc.y * rcp, acc.z * rcp, acc.w * rcp);
+}
+
+// ---- C ABI -------------------------------------------------------------------
+static inline int nbins(const cb_dims *d) { return d->aheight * d->astride; }
+static inline dim3 grid2(const cb_dims *d) { return dim3(d->astride / 32, d->aheight / 8); }
+
+#define CHECK_DIM(d)                                                           \
+    CB_REQUIRE((d) && (d)->astride > 0 && (d)->astride % 32 == 0 &&            \
+               (d)->aheight > 0 && (d)->aheight % 16 == 0,                     \
+               "dims must come from cb_calc_dim")
+
+#define POINTWISE(kernel, ...)                                                 \
+    do {                                                                       \
+        CHECK_DIM(dim);                                                        \
+        kernel<<<nbins(dim) / 256, 256, 0, cb_cs(s)>>>(__VA_ARGS__);           \
+        CB_LAUNCH_CHECK();                                                     \
+        return CB_OK;                                                          \
+    } while (0)
+
+extern "C" {
+
+int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s) {
+    POINTWISE(k_yuv_to_rgb, cb_ptr<float4>(dst), cb_ptr<const float4>(src));
+}
+
+int cb_logscale(cb_dptr dst4, cb_dptr src4, float k1, float k2, const cb_dims *dim,
+                cb_stream s) {
+    POINTWISE(k_logscale, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), k1, k2);
+}
+
+int cb_logencode(cb_dptr dst4, cb_dptr src4, float degamma, const cb_dims *dim,
+                 cb_stream s) {
+    POINTWISE(k_logencode, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), degamma);
+}
+
+int cb_apply_gamma(cb_dptr dst1, cb_dptr src4, float gamma, const cb_dims *dim,
+                   cb_stream s) {
+    POINTWISE(k_apply_gamma, cb_ptr<float>(dst1), cb_ptr<const float4>(src4), gamma);
+}
+
+int cb_haloclip(cb_dptr pix4, cb_dptr den1, float gamma_m_1, const cb_dims *dim,
+                cb_stream s) {
+    POINTWISE(k_haloclip, cb_ptr<float4>(pix4), cb_ptr<const float>(den1), gamma_m_1);
+}
+
+int cb_apply_gamma_full_hi(cb_dptr dst4, cb_dptr src4, float gamma_m_1,
+                           const cb_dims *dim, cb_stream s) {
+    POINTWISE(k_apply_gamma_full_hi, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4),
+              gamma_m_1);
+}
+
+int cb_smearclip(cb_dptr pix4, cb_dptr smear4, float gamma_m_1, float linrange,
+                 float lingam, const cb_dims *dim, cb_stream s) {
+    POINTWISE(k_smearclip, cb_ptr<float4>(pix4), cb_ptr<const float4>(smear4),
+              gamma_m_1, linrange, lingam);
+}
+
+int cb_plainclip(cb_dptr pix4, float gamma_m_1, float linrange, float lingam,
+                 float brightness, const cb_dims *dim, cb_stream s) {
+    POINTWISE(k_plainclip, cb_ptr<float4>(pix4), gamma_m_1, linrange, lingam, brightness);
+}
+
+int cb_colorclip(cb_dptr pix4, float vibrance, float highpow, float gamma,
+                 float linrange, float lingam, const cb_dims *dim, cb_stream s) {
+    POINTWISE(k_colorclip, cb_ptr<float4>(pix4), vibrance, highpow, gamma, linrange,
+              lingam);
+}
+
+static coefs7 load_coefs(const float c[7]) {
+    coefs7 k;
+    for (int i = 0; i < 7; i++) k.c[i] = c[i];
+    return k;
+}
+
+int cb_den_blur(cb_dptr dst1, cb_dptr src4, int pattern, int upsample,
+                const float coefs[7], const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(pattern >= 0 && pattern < 16 && coefs, "bad blur arguments");
+    k_den_blur<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+        cb_ptr<float>(dst1), cb_ptr<const float4>(src4), pattern, upsample,
+        load_coefs(coefs), *dim);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_den_blur_1c(cb_dptr dst1, cb_dptr src1, int pattern, int upsample,
+                   const float coefs[7], const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(pattern >= 0 && pattern < 16 && coefs, "bad blur arguments");
+    k_den_blur_1c<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+        cb_ptr<float>(dst1), cb_ptr<const float>(src1), pattern, upsample,
+        load_coefs(coefs), *dim);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_full_blur(cb_dptr dst4, cb_dptr src4, int pattern, int upsample,
+                 const float coefs[7], const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(pattern >= 0 && pattern < 16 && coefs, "bad blur arguments");
+    k_full_blur<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+        cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), pattern, upsample,
+        load_coefs(coefs), *dim);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern, int radius,
+                 float sstd, float cstd, float dstd, float dpow, float gspeed,
+                 const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(pattern >= 0 && pattern < 16, "bad direction");
+    CB_REQUIRE(radius >= 0 && radius < 32, "radius must be below 32");
+    k_bilateral<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+        cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), cb_ptr<const float>(blur1),
+        pattern, radius, sstd, cstd, dstd, dpow, gspeed, *dim);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+}  // extern "C"

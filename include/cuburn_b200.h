@@ -1,0 +1,200 @@
+/*
+ * cuburn_b200 -- C ABI of the B200 (sm_100a) render hot path.
+ *
+ * The reference renderer has no FFI of its own: its host code
+ * (cuburn/render.py, cuburn/filters.py, cuburn/output.py) drives named CUDA
+ * kernels through PyCUDA.  This library sits exactly where PyCUDA sits: device
+ * memory / streams / events, run-time compilation of the per-genome iterate
+ * module (NVRTC, sm_100a), and one entry point per kernel of the path.  Every
+ * entry point below names the reference call site or kernel it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns CB_OK (0) or a negative cb_status; the message of
+ *     the last failure on the calling thread is available from cb_last_error()
+ *   - device pointers are passed as uint64_t (cb_dptr); host pointers are plain
+ *   - all launches are asynchronous on the given stream; only cb_stream_sync,
+ *     cb_event_sync and cb_device_sync block
+ *   - not thread-safe per device, like the reference (render.py:401-402)
+ */
+#ifndef CUBURN_B200_H
+#define CUBURN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t cb_dptr;
+typedef struct cb_stream_s *cb_stream;
+typedef struct cb_event_s *cb_event;
+typedef struct cb_module_s *cb_module;
+
+typedef enum {
+    CB_OK = 0,
+    CB_ERR_CUDA = -1,        /* CUDA runtime / driver failure */
+    CB_ERR_NVRTC = -2,       /* run-time compilation failed; log in cb_last_error */
+    CB_ERR_INVALID = -3,     /* bad argument */
+    CB_ERR_NOMEM = -4,       /* device or pinned host allocation failed
+                                (pycuda MemoryError, render.py:140-147) */
+    CB_ERR_NOT_READY = 1     /* cb_event_query: work still in flight */
+} cb_status;
+
+/* Accumulation-buffer geometry (render.py:80-89 Framebuffers.calc_dim):
+ * gutter 12, awidth = width + 24, aheight = 16*ceil((height+24)/16),
+ * astride = 32*ceil(awidth/32). */
+typedef struct {
+    int32_t width, height, awidth, aheight, astride;
+} cb_dims;
+
+/* ---- library / device --------------------------------------------------- */
+const char *cb_last_error(void);
+const char *cb_version(void);
+int cb_device_count(int *count);                          /* main.py:96-107 */
+int cb_device_info(int device, char *name, size_t name_len, int *cc_major,
+                   int *cc_minor, int *sm_count, size_t *total_mem,
+                   size_t *l2_bytes);
+int cb_init(int device);                                  /* main.py:38-41 */
+int cb_device_sync(void);
+int cb_calc_dim(int width, int height, cb_dims *out);     /* render.py:80-89 */
+
+/* ---- memory, streams, events (PyCUDA driver calls, SURVEY 8b index) ------- */
+int cb_malloc(size_t bytes, cb_dptr *out);                /* render.py:133-138 */
+int cb_free(cb_dptr p);
+int cb_host_alloc(size_t bytes, void **out);              /* pinned; render.py:93 */
+int cb_host_free(void *p);
+int cb_stream_create(cb_stream *out);                     /* render.py:92,261 */
+int cb_stream_destroy(cb_stream s);
+int cb_stream_sync(cb_stream s);
+int cb_stream_wait_event(cb_stream s, cb_event e);        /* render.py:359,372 */
+int cb_event_create(cb_event *out);
+int cb_event_destroy(cb_event e);
+int cb_event_record(cb_event e, cb_stream s);
+int cb_event_query(cb_event e);                           /* CB_OK | CB_ERR_NOT_READY */
+int cb_event_sync(cb_event e);
+int cb_event_elapsed_ms(cb_event start, cb_event stop, float *ms);
+int cb_memcpy_h2d(cb_dptr dst, const void *src, size_t bytes, cb_stream s);
+int cb_memcpy_d2h(void *dst, cb_dptr src, size_t bytes, cb_stream s);
+int cb_memcpy_d2d(cb_dptr dst, cb_dptr src, size_t bytes, cb_stream s);
+/* 32-bit fill usable in a stream (code/util.py:240-263 fill_dptr) */
+int cb_fill32(cb_dptr dst, size_t nwords, uint32_t value, cb_stream s);
+
+/* ---- MWC RNG (code/mwc.py) ---------------------------------------------- */
+/* test_mwc (code/mwc.py:81-87): every stream advances `rounds` steps, the sum
+ * of its outputs goes to sums[i] (u64) and the state is written back. */
+int cb_mwc_test(cb_dptr seeds, int nstreams, int rounds, cb_dptr sums,
+                cb_stream s);
+
+/* ---- genome interpolation (code/interp.py) ------------------------------- */
+/* Catmull-Rom evaluation of every packed knot row at every temporal sample
+ * (catmull_rom / catmull_rom_mag, interp.py:295-366).  vals[ts][row] =
+ * spline_row(tstart + ts*tstep); row_mag[row] != 0 selects the magnitude
+ * domain.  times/knots are [nrows][32] float. */
+int cb_interp_rows(cb_dptr vals, cb_dptr times, cb_dptr knots, cb_dptr row_mag,
+                   int nrows, float tstart, float tstep, int nts, cb_stream s);
+/* The precalc stage of interp_iter_params (interp.py:235-271 + the precalc
+ * hunks in code/iter.py:12-30,56-95 and code/variations.py): runs the packed
+ * precalc program (int32 [nops][12], see cuburn_b200/code/packer.py) for each
+ * temporal sample, reading vals[ts][*] and writing params[ts][0..nslots). */
+int cb_interp_params(cb_dptr params, int param_stride, cb_dptr vals, int nrows,
+                     cb_dptr program, int nops, const cb_dims *dim, int nts,
+                     cb_stream s);
+/* interp_palette_flat (interp.py:372-433): palette row r (of nrows_out) is the
+ * blend in YUV of the two palettes around t = tstart + r*tstep, biased by +0.5
+ * in U,V, dithered by +-0.49 and quantised to 8 bits.  Output is float4
+ * [nrows_out][256] = (Y,U,V)/255 and 1.0 (the unit the float4 histogram
+ * accumulates, iter.py:395-406).  Entry (r, c) draws from RNG stream r*256+c. */
+int cb_interp_palette(cb_dptr palette_out, cb_dptr seeds, cb_dptr ptimes,
+                      cb_dptr pals, float tstart, float tstep, int nrows_out,
+                      cb_stream s);
+
+/* ---- per-genome iterate module (code/iter.py, render.py:232-246) --------- */
+/* Compile CUDA source for sm_100a with NVRTC and load it.  `headers` /
+ * `header_names` are in-memory include files.  On failure the NVRTC log is the
+ * cb_last_error() text. */
+int cb_module_build(const char *source, const char *name,
+                    const char *const *headers, const char *const *header_names,
+                    int nheaders, const char *const *options, int noptions,
+                    cb_module *out);
+int cb_module_destroy(cb_module m);
+int cb_module_get_cubin(cb_module m, const void **cubin, size_t *size);
+/* registers / static shared memory / max resident CTAs per SM of a kernel */
+int cb_module_kernel_info(cb_module m, const char *kernel, int block_threads,
+                          int *num_regs, int *static_smem, int *ctas_per_sm);
+/* Generic launch of a kernel of a built module: args is an array of pointers
+ * to the argument values (cuLaunchKernel convention). */
+int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,
+                     int bx, int by, int bz, int dyn_smem, void **args,
+                     cb_stream s);
+
+typedef struct {
+    cb_dptr hist;        /* float4 [aheight][astride] accumulation buffer */
+    cb_dptr seeds;       /* mwc_st [nstreams] */
+    cb_dptr points;      /* float4 [nstreams] trajectory state (x, y, color, -) */
+    cb_dptr params;      /* float [nts][param_stride] from cb_interp_params */
+    cb_dptr palette;     /* float4 [pal_rows][256] from cb_interp_palette */
+    cb_dims dim;
+    int32_t param_stride;
+    int32_t nts;         /* temporal samples (1024, render.py:207) */
+    int32_t pal_rows;    /* palette rows (64, render.py:202) */
+    int32_t fuse_rounds; /* >0: reseed all points and run this many unrecorded
+                            rounds first (iter.py:211-216) */
+    uint64_t first_sample;   /* global index of the first sample of this call */
+    uint64_t nsamples;       /* samples (recorded xform applications) to run */
+    uint64_t total_samples;  /* samples of the whole frame, all calls/GPUs */
+} cb_iter_args;
+/* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
+ * accumulated into hist.  grid_ctas persistent CTAs of 256 threads. */
+int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas,
+               cb_stream s);
+
+/* ---- filters (code/filters.py; host recipes in cuburn/filters.py) -------- */
+int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s);
+int cb_den_blur(cb_dptr dst1, cb_dptr src4, int pattern, int upsample,
+                const float coefs[7], const cb_dims *dim, cb_stream s);
+int cb_den_blur_1c(cb_dptr dst1, cb_dptr src1, int pattern, int upsample,
+                   const float coefs[7], const cb_dims *dim, cb_stream s);
+int cb_full_blur(cb_dptr dst4, cb_dptr src4, int pattern, int upsample,
+                 const float coefs[7], const cb_dims *dim, cb_stream s);
+int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern,
+                 int radius, float sstd, float cstd, float dstd, float dpow,
+                 float gspeed, const cb_dims *dim, cb_stream s);
+int cb_logscale(cb_dptr dst4, cb_dptr src4, float k1, float k2,
+                const cb_dims *dim, cb_stream s);
+int cb_apply_gamma(cb_dptr dst1, cb_dptr src4, float gamma, const cb_dims *dim,
+                   cb_stream s);
+int cb_haloclip(cb_dptr pix4, cb_dptr den1, float gamma_m_1, const cb_dims *dim,
+                cb_stream s);
+int cb_apply_gamma_full_hi(cb_dptr dst4, cb_dptr src4, float gamma_m_1,
+                           const cb_dims *dim, cb_stream s);
+int cb_smearclip(cb_dptr pix4, cb_dptr smear4, float gamma_m_1, float linrange,
+                 float lingam, const cb_dims *dim, cb_stream s);
+int cb_plainclip(cb_dptr pix4, float gamma_m_1, float linrange, float lingam,
+                 float brightness, const cb_dims *dim, cb_stream s);
+int cb_colorclip(cb_dptr pix4, float vibrance, float highpow, float gamma,
+                 float linrange, float lingam, const cb_dims *dim, cb_stream s);
+int cb_logencode(cb_dptr dst4, cb_dptr src4, float degamma, const cb_dims *dim,
+                 cb_stream s);
+
+/* ---- pixel-format output (code/output.py; launchC in output.py:21-26) ----- */
+typedef enum {
+    CB_FMT_RGBA_U8 = 0,     /* f32_to_rgba_u8   code/output.py:20-44   */
+    CB_FMT_RGBA_U16 = 1,    /* f32_to_rgba_u16  code/output.py:47-71   */
+    CB_FMT_YUV444P = 2,     /* f32_to_yuv444p   code/output.py:75-102  */
+    CB_FMT_YUV444P10 = 3,   /* f32_to_yuv444p10 code/output.py:106-134 */
+    CB_FMT_YUV420P10 = 4,   /* f32_to_yuv420p10 code/output.py:138-190 */
+    CB_FMT_YUV444P12 = 5    /* f32_to_yuv444p12 code/output.py:194-225 */
+} cb_pixfmt;
+/* Crop the gutter, convert and dither-quantise src (float4 [ah][astride]) into
+ * dst.  Pixel i (row-major over width x height) is produced by RNG stream
+ * i % nstreams, each stream walking its pixels in increasing order. */
+int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
+               const cb_dims *dim, cb_dptr seeds, int nstreams, cb_stream s);
+int cb_convert_size(cb_pixfmt fmt, const cb_dims *dim, size_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBURN_B200_H */
