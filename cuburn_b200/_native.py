@@ -318,39 +318,36 @@ def fill32(dst, nwords, value=0, stream=None):
 
 class PinnedPool(object):
     """
-    Page-locked host arrays, recycled by size (stands in for
-    pycuda.tools.PageLockedMemoryPool, render.py:93).
+    Page-locked host arrays, recycled by size once the array (and every view
+    of it) has been garbage collected -- stands in for
+    pycuda.tools.PageLockedMemoryPool (render.py:93).
     """
     def __init__(self):
         self._free = {}
         self._all = []
 
     def allocate(self, shape, dtype):
+        import weakref
         dtype = np.dtype(dtype)
-        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
-        nbytes = int(np.prod(shape)) * dtype.itemsize
-        bucket = self._free.get(nbytes)
+        if not isinstance(shape, (tuple, list)):
+            shape = (shape,)
+        shape = tuple(int(s) for s in shape)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        bucket = self._free.setdefault(nbytes, [])
         if bucket:
             raw = bucket.pop()
         else:
             p = c_void_p()
-            check(lib().cb_host_alloc(max(nbytes, 1), byref(p)))
-            raw = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
-            raw._cb_ptr = p.value
-            self._all.append(raw)
-        arr = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        return arr
-
-    def release(self, arr):
-        base = arr
-        while getattr(base, 'base', None) is not None and not isinstance(base, ctypes.Array):
-            base = base.base
-        if isinstance(base, ctypes.Array):
-            self._free.setdefault(ctypes.sizeof(base), []).append(base)
+            check(lib().cb_host_alloc(nbytes, byref(p)))
+            raw = (ctypes.c_char * nbytes).from_address(p.value)
+            self._all.append((raw, p.value))
+        root = np.frombuffer(raw, dtype=np.uint8)
+        weakref.finalize(root, bucket.append, raw)
+        return root[:int(np.prod(shape)) * dtype.itemsize].view(dtype).reshape(shape)
 
     def free_all(self):
-        for raw in self._all:
-            lib().cb_host_free(c_void_p(raw._cb_ptr))
+        for raw, ptr in self._all:
+            lib().cb_host_free(c_void_p(ptr))
         self._all, self._free = [], {}
 
 

@@ -66,6 +66,25 @@ __device__ __forceinline__ void reseed_point(float &x, float &y, float &c, mwc_s
     c = mwc_next_01(rng);
 }
 
+
+// Camera affine + round-to-nearest-even binning (iter.py:302-317, trunca in
+// code/util.py:194-200).  The unsigned compare also rejects negative
+// coordinates; the x bound is astride, not awidth, as in the reference.
+__device__ __forceinline__ int sample_bin(const float *P, float x, float y,
+                                          int astride, int aheight) {
+    float cx = __fmaf_rn(P[CAM_XX], x, __fmaf_rn(P[CAM_XY], y, P[CAM_XO]));
+    float cy = __fmaf_rn(P[CAM_YX], x, __fmaf_rn(P[CAM_YY], y, P[CAM_YO]));
+    unsigned int ix = (unsigned int)__float2int_rn(cx);
+    unsigned int iy = (unsigned int)__float2int_rn(cy);
+    if (ix >= (unsigned int)astride || iy >= (unsigned int)aheight) return -1;
+    return (int)(iy * (unsigned int)astride + ix);
+}
+
+// Palette column: rni(color * 255 + dither), clamped to the table (iter.py:346-351).
+__device__ __forceinline__ unsigned int color_index(float color, float dither) {
+    return min(__float2uint_rn(__fmaf_rn(color, 255.0f, dither)), 255u);
+}
+
 // Exchange buffers: structure-of-arrays so that both the permuted write and the
 // linear read are bank-conflict free.
 struct xchg_buf {
@@ -165,19 +184,42 @@ cb_iter(const __grid_constant__ iter_args a) {
 #if HAS_FINAL
             final_step(P, fx, fy, fc, rng);
 #endif
-            float cx = __fmaf_rn(P[CAM_XX], fx, __fmaf_rn(P[CAM_XY], fy, P[CAM_XO]));
-            float cy = __fmaf_rn(P[CAM_YX], fx, __fmaf_rn(P[CAM_YY], fy, P[CAM_YO]));
-            // round to nearest even; the unsigned compare also rejects negatives
-            unsigned int ix = (unsigned int)__float2int_rn(cx);
-            unsigned int iy = (unsigned int)__float2int_rn(cy);
-            if (ix >= (unsigned int)a.dim.astride || iy >= (unsigned int)a.dim.aheight)
-                continue;
-            unsigned int ci = min(__float2uint_rn(__fmaf_rn(fc, 255.0f, color_dither)), 255u);
-            float4 col = __ldg(pal + ci);
-            red_add_f32x4(a.hist + (size_t)iy * a.dim.astride + ix, col);
+            int bin = sample_bin(P, fx, fy, a.dim.astride, a.dim.aheight);
+            if (bin < 0) continue;
+            float4 col = __ldg(pal + color_index(fc, color_dither));
+            red_add_f32x4(a.hist + bin, col);
         }
     }
 
     a.points[gtid] = make_float4(x, y, c, 0.0f);
     a.seeds[gtid] = rng;
+}
+
+// ---- probes used by the parity tests -------------------------------------------
+// Apply the genome's weighted choice with a given selector to explicit points.
+extern "C" __global__ void cb_probe_xform(const float *params, float *xs, float *ys,
+                                          float *cs, mwc_st *seeds, int n, float sel,
+                                          int use_final) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mwc_st rng = seeds[i];
+    float x = xs[i], y = ys[i], c = cs[i];
+#if HAS_FINAL
+    if (use_final) final_step(params, x, y, c, rng);
+    else
+#endif
+        chaos_step(params, sel, x, y, c, rng);
+    xs[i] = x; ys[i] = y; cs[i] = c;
+    seeds[i] = rng;
+}
+
+// Camera + binning + palette column for explicit points.
+extern "C" __global__ void cb_probe_bins(const float *params, const float *xs,
+                                         const float *ys, const float *cs,
+                                         const float *dithers, int n, int astride,
+                                         int aheight, int *bins, int *cidx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bins[i] = sample_bin(params, xs[i], ys[i], astride, aheight);
+    cidx[i] = (int)color_index(cs[i], dithers[i]);
 }

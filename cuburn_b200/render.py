@@ -1,0 +1,330 @@
+"""
+Render orchestration: device buffers, the per-genome compiled module, and the
+per-frame launch sequence  interpolate -> iterate -> filter chain -> convert ->
+copy to host.
+
+Keeps the reference surface (cuburn/render.py): ``Framebuffers`` (with
+``calc_dim / set_dim / alloc / free / flip / flip_side`` and ``gutter == 12``),
+``DevSrc``, ``DevInfo``, ``Renderer(gnm, gprof, keep=False, arch=None)`` with
+``.packer .lib .cubin .mod .filts .out``, ``RenderManager.queue_frame(rdr, gnm,
+gprof, tc, copy=True) -> (evt, h_out)`` where ``evt.query() / synchronize() /
+time()``.  Everything below the Python surface goes through the C ABI
+(_native.py); nothing here computes pixels on the CPU.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from . import _native as N
+from . import filters, output, mwc
+from .code import itergen, packer as packer_mod
+from .genome.util import palette_decode
+
+RenderedImage = namedtuple('RenderedImage', 'buf idx gpu_time')
+Dimensions = N.Dims
+
+# Samples one CTA processes between parameter reloads (256 threads x 256
+# rounds; the reference's block lifetime, iter.py:218).
+UNIT_SAMPLES = 65536
+ITER_THREADS = 256
+
+
+class DurationEvent(N.Event):
+    """An event that remembers a prior event to measure from (render.py:26-38)."""
+    def __init__(self, prior):
+        super().__init__()
+        self._prior = prior
+
+    def time(self):
+        return self.time_since(self._prior)
+
+
+class Framebuffers(object):
+    """
+    The large device allocations (render.py:40-170).  ``d_front`` / ``d_back``
+    / ``d_left`` / ``d_right`` hold one float4 per accumulation bin.  A filter
+    may use any of them as long as its result ends up in ``d_front``;
+    ``Output.convert`` writes ``d_back``.
+
+    The chaos game accumulates straight into ``d_front`` (float4 atomics), so
+    the reference's packed integer side buffers and hotspot flag planes
+    (``d_uleft`` / ``d_uright``) have no job here; the attributes exist for
+    API compatibility and stay ``None``.
+    """
+    gutter = 12
+
+    # RNG streams / trajectories available to any kernel.  The multiplier
+    # table has 262144 entries (= 1024 ring slots x 256 in the reference,
+    # render.py:100-104).
+    nstreams = 262144
+
+    @classmethod
+    def calc_dim(cls, width, height):
+        return N.calc_dim(width, height)
+
+    def __init__(self, seed=None):
+        N.ensure_init()
+        self.stream = N.Stream()
+        self.pool = N.PinnedPool()
+        self._clear()
+        seeds = mwc.make_seeds(self.nstreams, host_seed=seed)
+        self.d_seeds = N.to_device(seeds)
+        self._len_d_points = self.nstreams * 16
+        self.d_points = N.DeviceBuffer(self._len_d_points)
+        N.fill32(self.d_points, self._len_d_points // 4, np.float32(np.nan))
+        N.check(N.lib().cb_device_sync())
+
+    def reseed(self, seed):
+        """Reset every RNG stream as ``make_seeds(nstreams, host_seed=seed)``."""
+        N.memcpy_htod(self.d_seeds, mwc.make_seeds(self.nstreams, host_seed=seed))
+
+    def _clear(self):
+        self.nbins = None
+        self.d_front = self.d_back = self.d_left = self.d_right = None
+        self.d_uleft = self.d_uright = None
+
+    def free(self, stream=None):
+        if stream is not None:
+            stream.synchronize()
+        else:
+            N.check(N.lib().cb_device_sync())
+        for p in (self.d_front, self.d_back, self.d_left, self.d_right):
+            if p is not None:
+                p.free()
+        self._clear()
+
+    def alloc(self, dim, stream=None):
+        nbins = dim.ah * dim.astride
+        if self.nbins is not None and self.nbins >= nbins:
+            return
+        if self.nbins is not None:
+            self.free(stream)
+        try:
+            self.d_front = N.DeviceBuffer(16 * nbins)
+            self.d_back = N.DeviceBuffer(16 * nbins)
+            self.d_left = N.DeviceBuffer(16 * nbins)
+            self.d_right = N.DeviceBuffer(16 * nbins)
+            self.nbins = nbins
+        except MemoryError:
+            self.free(stream)
+            raise
+
+    def set_dim(self, width, height, stream=None):
+        dim = self.calc_dim(width, height)
+        self.alloc(dim, stream)
+        return dim
+
+    def flip(self):
+        self.d_front, self.d_back = self.d_back, self.d_front
+
+    def flip_side(self):
+        self.d_left, self.d_right = self.d_right, self.d_left
+        self.d_uleft, self.d_uright = self.d_uright, self.d_uleft
+
+
+class DevSrc(object):
+    """Device copies of the genome's interpolation sources (render.py:172-190)."""
+    max_knots = packer_mod.MAX_KNOTS
+    max_params = 1024
+
+    def __init__(self):
+        self.d_times = N.DeviceBuffer(4 * self.max_knots * self.max_params)
+        self.d_knots = N.DeviceBuffer(4 * self.max_knots * self.max_params)
+        self.d_ptimes = N.DeviceBuffer(4 * self.max_knots)
+        self.d_pals = N.DeviceBuffer(4 * 4 * 256 * self.max_knots)
+        self.d_row_mag = N.DeviceBuffer(4 * self.max_params)
+        self.d_program = N.DeviceBuffer(4 * packer_mod.PROG_WIDTH * 2 * self.max_params)
+
+
+class DevInfo(object):
+    """Per-frame temporal samples on the device (render.py:192-223)."""
+    palette_width = 256
+    palette_height = 64
+    ntemporal_samples = 1024
+    # unrecorded settling rounds for freshly seeded trajectories
+    fuse = 32
+
+    def __init__(self):
+        nts = self.ntemporal_samples
+        self.d_params = N.DeviceBuffer(nts * DevSrc.max_params * 4)
+        self.d_vals = N.DeviceBuffer(nts * DevSrc.max_params * 4)
+        self.d_palette = N.DeviceBuffer(self.palette_height * self.palette_width * 16)
+
+
+class Renderer(object):
+    """
+    A genome structure compiled for the device, plus its filter chain and
+    output module (render.py:225-251).  Modules are cached by generated source,
+    so genomes that share a structure share a module.
+    """
+    MAX_MODREFS = 20
+    _modrefs = {}
+
+    @classmethod
+    def compile(cls, gnm, arch=None, keep=False):
+        pk, src = itergen.mkiterlib(gnm)
+        mod = cls._modrefs.get(src)
+        if mod is None:
+            names, hdrs = itergen.load_headers()
+            mod = N.Module(src, 'iter.cu', hdrs, names, itergen.NVRTC_OPTIONS)
+            if len(cls._modrefs) > cls.MAX_MODREFS:
+                cls._modrefs.clear()
+            cls._modrefs[src] = mod
+        if keep:
+            import os, tempfile
+            base = os.path.join(tempfile.gettempdir(), 'iter_kern')
+            with open(base + '.cu', 'w') as fp:
+                fp.write(src)
+            with open(base + '.cubin', 'wb') as fp:
+                fp.write(mod.cubin)
+        return pk, src, mod
+
+    def __init__(self, gnm, gprof, keep=False, arch=None):
+        self.packer, self.lib, self.mod = self.compile(gnm, arch=arch, keep=keep)
+        self.filts = filters.create(gprof)
+        self.out = output.get_output_for_profile(gprof)
+        self._grid = None
+
+    @property
+    def cubin(self):
+        return self.mod.cubin
+
+    def grid_ctas(self, nstreams):
+        """Persistent grid: every SM filled to the kernel's occupancy."""
+        if self._grid is None:
+            info = self.mod.kernel_info('cb_iter', ITER_THREADS)
+            sms = N.device_info(N._initialised or 0)['sm_count']
+            self.kernel_info = info
+            self._grid = max(1, min(info['ctas_per_sm'] * sms, nstreams // ITER_THREADS))
+        return self._grid
+
+
+class RenderManager(object):
+    """Queues frames on the device (render.py:253-434)."""
+    def __init__(self, seed=None):
+        N.ensure_init()
+        self.fb = Framebuffers(seed=seed)
+        self.src_a, self.src_b = DevSrc(), DevSrc()
+        self.info_a, self.info_b = DevInfo(), DevInfo()
+        self.stream_a, self.stream_b = N.Stream(), N.Stream()
+        self.filt_evt = self.copy_evt = None
+        # share of the frame's samples this manager renders (multi-GPU stills)
+        self.sample_share = (0, 1)
+        self.hist_hook = None
+
+    # -- upload ----------------------------------------------------------------
+    def _copy(self, rdr, gnm):
+        """H2D: knot rows, palettes and the precalc program (render.py:264-285)."""
+        pk = rdr.packer
+        if pk.nrows > DevSrc.max_params or pk.nslots > DevSrc.max_params:
+            raise ValueError('genome needs %d rows / %d slots; limit is %d'
+                             % (pk.nrows, pk.nslots, DevSrc.max_params))
+        pool, s, src = self.fb.pool, self.stream_a, self.src_a
+        times = pool.allocate((pk.nrows, pk_width()), 'f4')
+        knots = pool.allocate((pk.nrows, pk_width()), 'f4')
+        pk.pack(gnm, times, knots)
+        N.memcpy_htod(src.d_times, times, s)
+        N.memcpy_htod(src.d_knots, knots, s)
+
+        palsrc = dict((v[0], palette_decode(v[1:])) for v in gnm['palette'])
+        if len(palsrc) > DevSrc.max_knots:
+            raise ValueError('too many palettes')
+        ptimes, pvals = zip(*sorted(palsrc.items()))
+        palettes = pool.allocate((len(palsrc), 256, 4), 'f4')
+        palettes[:] = pvals
+        palette_times = pool.allocate((DevSrc.max_knots,), 'f4')
+        palette_times.fill(1e9)
+        palette_times[:len(ptimes)] = ptimes
+        N.memcpy_htod(src.d_pals, palettes, s)
+        N.memcpy_htod(src.d_ptimes, palette_times, s)
+
+        mag = pool.allocate((pk.nrows,), 'i4')
+        mag[:] = pk.row_mag
+        prog = pool.allocate(pk.program_array().shape, 'i4')
+        prog[:] = pk.program_array()
+        N.memcpy_htod(src.d_row_mag, mag, s)
+        N.memcpy_htod(src.d_program, prog, s)
+        self._pinned = (times, knots, palettes, palette_times, mag, prog)
+
+    # -- interpolate -------------------------------------------------------------
+    def _interp(self, rdr, gnm, dim, ts, td):
+        L, s, info, src, pk = N.lib(), self.stream_a, self.info_a, self.src_a, rdr.packer
+        N.check(L.cb_interp_palette(
+            info.d_palette.ptr, self.fb.d_seeds.ptr, src.d_ptimes.ptr, src.d_pals.ptr,
+            np.float32(ts), np.float32(td / info.palette_height), info.palette_height,
+            s.handle))
+        nts = info.ntemporal_samples
+        N.check(L.cb_interp_rows(
+            info.d_vals.ptr, src.d_times.ptr, src.d_knots.ptr, src.d_row_mag.ptr,
+            pk.nrows, np.float32(ts), np.float32(td / nts), nts, s.handle))
+        N.check(L.cb_interp_params(
+            info.d_params.ptr, pk.param_stride, info.d_vals.ptr, pk.nrows,
+            src.d_program.ptr, len(pk.program), N.byref(dim), nts, s.handle))
+
+    # -- iterate -------------------------------------------------------------------
+    def frame_samples(self, gprof, dim, tc):
+        """Samples for the whole frame (render.py:331), and this manager's share."""
+        total = int(gprof.spp(tc) * dim.w * dim.h)
+        rank, world = self.sample_share
+        units = (total + UNIT_SAMPLES - 1) // UNIT_SAMPLES
+        lo = units * rank // world
+        hi = units * (rank + 1) // world
+        first = lo * UNIT_SAMPLES
+        n = min(hi * UNIT_SAMPLES, total) - first
+        return total, first, max(n, 0)
+
+    def _iter(self, rdr, gnm, gprof, dim, tc):
+        s, info = self.stream_a, self.info_a
+        nbins = dim.ah * dim.astride
+        N.fill32(self.fb.d_front, 4 * nbins, 0, s)
+        total, first, n = self.frame_samples(gprof, dim, tc)
+        args = N.IterArgs(
+            hist=self.fb.d_front.ptr, seeds=self.fb.d_seeds.ptr,
+            points=self.fb.d_points.ptr, params=info.d_params.ptr,
+            palette=info.d_palette.ptr, dim=dim, param_stride=rdr.packer.param_stride,
+            nts=info.ntemporal_samples, pal_rows=info.palette_height,
+            fuse_rounds=info.fuse, first_sample=first, nsamples=n, total_samples=total)
+        N.check(N.lib().cb_iterate(rdr.mod.handle, N.byref(args),
+                                   rdr.grid_ctas(self.fb.nstreams), s.handle))
+        self.last_iter_samples = n
+
+    # -- frame -----------------------------------------------------------------------
+    def queue_frame(self, rdr, gnm, gprof, tc, copy=True):
+        """
+        Queue one frame; returns ``(evt, h_out)`` (render.py:374-434).  ``evt``
+        completes when ``h_out`` (pinned host memory in the output module's
+        format) is valid.  Not thread-safe.
+        """
+        timing_event = N.Event().record(self.stream_b)
+        dim = self.fb.set_dim(gprof.width, gprof.height, self.stream_b)
+
+        td = gprof.frame_width(tc) / round(gprof.fps * gprof.duration)
+        ts = tc - 0.5 * td
+
+        if copy:
+            self.src_a, self.src_b = self.src_b, self.src_a
+            self._copy(rdr, gnm)
+        self._interp(rdr, gnm, dim, ts, td)
+        if self.filt_evt:
+            self.stream_a.wait_for_event(self.filt_evt)
+        self._iter(rdr, gnm, gprof, dim, tc)
+        if self.hist_hook is not None:
+            # multi-GPU stills: combine per-GPU histograms before filtering
+            self.hist_hook(self.fb, dim, self.stream_a)
+        if self.copy_evt:
+            self.stream_a.wait_for_event(self.copy_evt)
+        for filt in rdr.filts:
+            params = getattr(gprof.filters, filt.name)
+            filt.apply(self.fb, gprof, params, dim, tc, self.stream_a)
+        rdr.out.convert(self.fb, gprof, dim, self.stream_a)
+        self.filt_evt = N.Event().record(self.stream_a)
+        h_out = rdr.out.copy(self.fb, dim, self.fb.pool, self.stream_a)
+        self.copy_evt = DurationEvent(timing_event).record(self.stream_a)
+
+        self.info_a, self.info_b = self.info_b, self.info_a
+        self.stream_a, self.stream_b = self.stream_b, self.stream_a
+        return self.copy_evt, h_out
+
+
+def pk_width():
+    return packer_mod.MAX_KNOTS

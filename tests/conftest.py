@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REFERENCE = '/root/reference'
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def native():
+    """The C-ABI library initialised on cuda:0 (GPU tests only)."""
+    from cuburn_b200 import _native as N
+    N.init(0)
+    return N
+
+
+@pytest.fixture(scope='session')
+def built():
+    """Make sure the native library, multiplier table and C oracle exist."""
+    from cuburn_b200.build import build_all
+    from oracle.build import build
+    build_all()
+    build()
+    return True
+
+
+def have_reference():
+    return os.path.isdir(os.path.join(REFERENCE, 'cuburn'))

@@ -1,0 +1,116 @@
+"""
+MWC RNG: the multiplier table, the reference's known-answer recurrence model
+(cuburn/code/mwc.py:90-129: numpy-u64 model, host_seed=42) against the oracle,
+and on the GPU against the device generator.
+"""
+import numpy as np
+import pytest
+
+from conftest import have_reference, REFERENCE
+
+
+def _numpy_model(seeds, rounds):
+    """The CPU model the reference's own self-test uses (code/mwc.py:105-113)."""
+    mults = seeds[:, 0].astype(np.uint64)
+    states = seeds[:, 1].astype(np.uint64)
+    carries = seeds[:, 2].astype(np.uint64)
+    sums = np.zeros(seeds.shape[0], np.uint64)
+    for _ in range(rounds):
+        step = mults * states + carries
+        states = step & np.uint64(0xffffffff)
+        carries = step >> np.uint64(32)
+        sums += states
+    return sums, states.astype(np.uint32), carries.astype(np.uint32)
+
+
+def test_multiplier_table(built):
+    from cuburn_b200 import mwc
+    m = mwc.load_mults()
+    assert m.shape == (262144,) and m.dtype == np.dtype('<u4')
+    assert m[0] == 0xffffff4e and m[-1] == 4103034564
+    assert np.all(np.diff(m.astype(np.int64)) < 0)
+    # spot-check the defining property on a few entries: a*2^32-1 and a*2^31-1 prime
+    def is_prime(n):
+        if n % 2 == 0:
+            return False
+        d, s = n - 1, 0
+        while d % 2 == 0:
+            d //= 2
+            s += 1
+        for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            x = pow(a, d, n)
+            if x in (1, n - 1):
+                continue
+            for _ in range(s - 1):
+                x = x * x % n
+                if x == n - 1:
+                    break
+            else:
+                return False
+        return True
+    for a in (int(m[0]), int(m[1]), int(m[1000]), int(m[-1])):
+        assert is_prime(a * 2 ** 32 - 1) and is_prime(a * 2 ** 31 - 1)
+
+
+@pytest.mark.skipif(not have_reference(), reason='reference tree not mounted')
+def test_multiplier_table_matches_reference(built):
+    from cuburn_b200 import mwc
+    ref = np.fromfile(REFERENCE + '/cuburn/code/primes.bin', dtype='<u4')
+    assert np.array_equal(ref, mwc.load_mults())
+
+
+def test_make_seeds_layout(built):
+    from cuburn_b200 import mwc
+    s = mwc.make_seeds(1024, host_seed=42)
+    assert s.shape == (1024, 3) and s.dtype == np.uint32
+    assert np.array_equal(s[:, 0], mwc.load_mults()[:1024])
+    rs = np.random.RandomState(42)
+    assert np.array_equal(s[:, 1], rs.randint(1, 0x7fffffff, size=1024).astype(np.uint32))
+    assert np.array_equal(s[:, 2], rs.randint(1, 0x7fffffff, size=1024).astype(np.uint32))
+
+
+def test_oracle_matches_reference_model(built):
+    from cuburn_b200 import mwc
+    from oracle import flame_ref as R
+    seeds = mwc.make_seeds(64 * 512, host_seed=42)
+    want, st, ca = _numpy_model(seeds, 500)
+    got, after = R.mwc_sums(seeds, 500)
+    assert np.array_equal(want, got)
+    assert np.array_equal(after[:, 1], st) and np.array_equal(after[:, 2], ca)
+    # the vectorised numpy streams used by the palette / output oracles agree too
+    streams = R.MwcStreams(seeds[:4096])
+    acc = np.zeros(4096, np.uint64)
+    for _ in range(50):
+        acc += streams.next_u32().astype(np.uint64)
+    want50, _, _ = _numpy_model(seeds[:4096], 50)
+    assert np.array_equal(acc, want50)
+
+
+def test_float_mappings(built):
+    from oracle import flame_ref as R
+    seeds = np.array([[4294967118, 1, 0], [4294967118, 0x80000000, 5]], np.uint32)
+    s = R.MwcStreams(seeds)
+    u = R.MwcStreams(seeds).next_u32()
+    f01 = s.next_01()
+    assert np.all((f01 >= 0) & (f01 <= 1))
+    assert f01[0] == np.float32(u[0]) * np.float32(2.0 ** -32)
+    s2 = R.MwcStreams(seeds)
+    f11 = s2.next_11()
+    assert f11[0] == np.float32(np.int32(u[0])) * np.float32(2.0 ** -31)
+
+
+@pytest.mark.gpu
+def test_device_mwc_matches_model(native, built):
+    """test_mwc (code/mwc.py:90-129): 64 x 512 streams, seed 42, 5000 rounds."""
+    N = native
+    from cuburn_b200 import mwc
+    n = 64 * 512
+    seeds = mwc.make_seeds(n, host_seed=42)
+    want, st, ca = _numpy_model(seeds, 5000)
+    d_seeds = N.to_device(seeds)
+    d_sums = N.DeviceBuffer(8 * n)
+    N.check(N.lib().cb_mwc_test(d_seeds.ptr, n, 5000, d_sums.ptr, None))
+    got = N.from_device(d_sums, (n,), np.uint64)
+    after = N.from_device(d_seeds, (n, 3), np.uint32)
+    assert np.array_equal(want, got)
+    assert np.array_equal(after[:, 1], st) and np.array_equal(after[:, 2], ca)
