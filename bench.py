@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""
+bench.py -- the reference's headline metric on its headline config.
+
+Metric: IFS iterations/s (BASELINE.json).  Workload (N=1): configs[1], the
+1080p still of the 6-xform + final-xform flame G6F at 2000 spp, synthetic
+genome (cuburn_b200/samples.py).  One *step* renders one frame on the device:
+interpolate the packed genome, run the chaos game, run the default filter
+chain (yuv, bilateral, logscale, smearclip) and convert to RGBA8.
+
+  value   samples / device time of the step, inputs resident in HBM
+  e2e     the same through RenderManager.queue_frame -- H2D of the packed
+          genome + palettes from pinned memory, D2H of the finished frame
+  N > 1   one process per GPU (torchrun); every GPU runs the config's sample
+          count with its own RNG streams (weak scaling: the still gets N x the
+          samples), the float4 histograms are summed onto rank 0 with one NCCL
+          reduce, rank 0 filters; time = max over ranks, device events.
+
+  --impl reference   the CPU oracle's chaos game (oracle/chaos.c, OpenMP on all
+          host cores) on a bounded sample of the same workload.  cuburn itself
+          is GPU-only Python 2 + PyCUDA and cannot run here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+CONFIG = dict(genome='G6F', width=1920, height=1080, spp=2000)
+UNIT = 65536
+
+
+def read_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fp:
+            return float(json.load(fp)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device=0):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown',
+                                  'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def frame_setup(n_gpus, rank, seed=1):
+    from cuburn_b200 import _native as N, samples, profile, render
+    gnm = samples.GENOMES[CONFIG['genome']]()
+    prof = dict(width=CONFIG['width'], height=CONFIG['height'],
+                spp=CONFIG['spp'] * n_gpus, frame_width=0, start=1, end=2)
+    gprof = profile.wrap(prof, gnm)
+    tc = profile.enumerate_times(gprof)[0][1][0]
+    rmgr = render.RenderManager(seed=seed, rank=rank, world=n_gpus)
+    rdr = render.Renderer(gnm, gprof)
+    return N, gnm, gprof, tc, rmgr, rdr
+
+
+def cpu_chaos_rate(nsamples, nthreads=0, seed=1):
+    """Oracle chaos game on the host cores: (iterations/s, threads used)."""
+    from cuburn_b200 import samples, mwc
+    from oracle import flame_ref as R
+    gnm = samples.GENOMES[CONFIG['genome']]()
+    w, h = CONFIG['width'], CONFIG['height']
+    ev = R.GenomeEval(gnm, w, h, 1.5 / 720, 0.0)
+    seeds = mwc.make_seeds(32768, host_seed=seed)
+    pal, seeds = R.palette_table(gnm, ev.ts, ev.td, seeds)
+    cores = nthreads or (os.cpu_count() or 1)
+    R.iterate(ev, pal, seeds, 2 ** 20, nthreads=cores)          # warm
+    t = time.perf_counter()
+    R.iterate(ev, pal, seeds, nsamples, nthreads=cores)
+    return nsamples / (time.perf_counter() - t), cores
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement, all host cores, bounded sample per step."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    sample_spp = 100                       # 2.07e8 samples per step, ~1-3 s on 8 cores
+    n = CONFIG['width'] * CONFIG['height'] * sample_spp
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, cores = cpu_chaos_rate(n)
+        if i >= args.warmup:
+            rates.append(r)
+    value = float(np.mean(rates))
+    line = {
+        'impl': 'reference', 'metric': 'ifs_iterations_per_second', 'value': value,
+        'unit': 'iterations/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * n / value, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '1080p still, G6F (6 xforms + final, 12 variation types), '
+                               '2000 spp; CPU arm runs a %d-spp sample per step' % sample_spp},
+        'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': cores,
+                         'kind': 'port',
+                         'sample': '%d samples (1080p x %d spp) of the chaos game per step'
+                                   % (n, sample_spp)},
+        'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
+
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    from cuburn_b200 import multigpu
+    rank, world, local = multigpu.env_rank_world()
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    n_gpus = world
+    dist = None
+    if n_gpus > 1:
+        import torch
+        import torch.distributed as dist
+        multigpu.init_process_group('nccl')
+
+    from cuburn_b200 import _native as N
+    N.init(local)
+    N_, gnm, gprof, tc, rmgr, rdr = frame_setup(n_gpus, rank)
+    reducer = None
+    if n_gpus > 1:
+        reducer = multigpu.HistReducer(root=0)
+        rmgr.hist_hook = reducer
+    dim = rmgr.fb.set_dim(gprof.width, gprof.height)
+    td = gprof.frame_width(tc) / round(gprof.fps * gprof.duration)
+    ts = tc - 0.5 * td
+    total, first, mine = rmgr.frame_samples(gprof, dim, tc)
+
+    # L2 flush buffer: 512 MiB > 126 MiB L2, written between timed steps
+    flush = N.DeviceBuffer(512 << 20)
+
+    def l2_flush():
+        N.fill32(flush, (512 << 20) // 4, 0, rmgr.stream_a)
+
+    def barrier():
+        rmgr.stream_a.synchronize()
+        rmgr.stream_b.synchronize()
+        N.check(N.lib().cb_device_sync())
+        if dist is not None:
+            dist.barrier()
+
+    def device_step(ev0, ev_iter0, ev_iter1, ev1):
+        """One frame with inputs resident: interp + iterate (+reduce) + filters + convert."""
+        s = rmgr.stream_a
+        ev0.record(s)
+        rmgr._interp(rdr, gnm, dim, ts, td)
+        ev_iter0.record(s)
+        rmgr._iter(rdr, gnm, gprof, dim, tc)
+        ev_iter1.record(s)
+        if reducer is not None:
+            reducer(rmgr.fb, dim, s)
+        if reducer is None or rank == 0:
+            for filt in rdr.filts:
+                filt.apply(rmgr.fb, gprof, getattr(gprof.filters, filt.name), dim, tc, s)
+            rdr.out.convert(rmgr.fb, gprof, dim, s)
+        ev1.record(s)
+
+    # ---- device-resident timing ----------------------------------------------------
+    rmgr._copy(rdr, gnm)
+    evs = [[N.Event() for _ in range(4)] for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        device_step(*[N.Event() for _ in range(4)])
+        l2_flush()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    step_ms, iter_ms = [], []
+    for k in range(args.steps):
+        l2_flush()
+        barrier()
+        device_step(*evs[k])
+        barrier()
+        step_ms.append(evs[k][3].time_since(evs[k][0]))
+        iter_ms.append(evs[k][2].time_since(evs[k][1]))
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = float(np.sum(step_ms))
+    if dist is not None:
+        import torch
+        t = torch.tensor([my_ms, float(np.sum(iter_ms))], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        my_ms, iter_total = float(t[0]), float(t[1])
+    else:
+        iter_total = float(np.sum(iter_ms))
+    ms_per_step = my_ms / args.steps
+    value = total / (ms_per_step * 1e-3)
+
+    # ---- end to end through queue_frame (host buffers in, host frame out) --------------
+    e2e_ms = []
+    for k in range(args.warmup + args.steps):
+        l2_flush()
+        barrier()
+        evt, buf = rmgr.queue_frame(rdr, gnm, gprof, tc, copy=True)
+        evt.synchronize()
+        barrier()
+        if k >= args.warmup:
+            e2e_ms.append(evt.time())
+    e2e_my = float(np.sum(e2e_ms))
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_my], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_my = float(t[0])
+    e2e_value = total / (e2e_my / args.steps * 1e-3)
+    pk = rdr.packer
+    h2d = 2 * pk.nrows * 32 * 4 + len(gnm['palette']) * 256 * 16 + 32 * 4 \
+        + pk.nrows * 4 + pk.program_array().nbytes
+    d2h = int(buf.nbytes)
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (cb_iter) -----------------------------------
+    peak, peak_src = read_peaks()
+    iter_ms_mean = iter_total / args.steps
+    algo_bytes = 16.0 * mine                     # one 16-byte float4 accumulate per sample
+    achieved = algo_bytes / (iter_ms_mean * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'cb_iter', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src,
+                'note': 'algorithmic bytes = 16 B float4 accumulate per sample; the 33 MiB '
+                        'histogram is L2-resident so the true bound is L2 atomic / issue rate, '
+                        'see profiles/',
+                'kernel_ms': iter_ms_mean,
+                'samples_per_second_kernel': mine / (iter_ms_mean * 1e-3)}
+    nbins = dim.ah * dim.astride
+    filt_ms = ms_per_step - iter_ms_mean
+    roofline_filters = {'bound': 'hbm', 'stage': 'interp + filter chain + convert',
+                        'algorithmic_bytes_per_bin': 804,
+                        'achieved': 804.0 * nbins / (filt_ms * 1e-3) / 1e9, 'peak': peak,
+                        'unit': 'GB/s', 'frac': 804.0 * nbins / (filt_ms * 1e-3) / 1e9 / peak,
+                        'ms': filt_ms}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_cpu = CONFIG['width'] * CONFIG['height'] * 500        # ~10-20 s of CPU work
+        rate, cores = cpu_chaos_rate(n_cpu)
+        cpu = {'value': rate, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d samples (1080p x 500 spp) of the same genome, chaos game only'
+                         % n_cpu}
+
+    launches_per_step = 4 + 1 + 1 + 8 * 3 + 1 + 6 + 1     # fill, 3 interp, iter, yuv, bilateral, logscale, smearclip, convert
+    line = {
+        'metric': 'ifs_iterations_per_second', 'value': value, 'unit': 'iterations/s',
+        'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '1080p still, G6F (6 xforms + final xform, 12 variation '
+                               'types), %d spp per GPU, default filter chain, RGBA8 out'
+                               % CONFIG['spp'],
+                   'samples_per_step': total, 'frames_per_second': 1e3 / ms_per_step,
+                   'l2': 'L2 flushed between timed steps (512 MiB fill)',
+                   'timing': 'CUDA events on the launching stream, per step, max over ranks',
+                   'parallelism': 'independent RNG streams per GPU + NCCL reduce'
+                                  if n_gpus > 1 else 'single GPU'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'iterations/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_my / args.steps},
+        'gpu_launches': launches_per_step * args.steps,
+        'roofline': roofline, 'roofline_filters': roofline_filters,
+        'cpu_baseline': cpu,
+        'wall_s_timed_region': wall,
+    }
+    if reducer is not None and reducer.reduce_ms:
+        line['config']['nccl_reduce_ms'] = float(np.mean(reducer.reduce_ms[-args.steps:]))
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

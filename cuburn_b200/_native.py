@@ -262,9 +262,6 @@ class DeviceBuffer(object):
         except Exception:
             pass
 
-    def __cuda_array_interface__(self):
-        raise AttributeError
-
     def view(self, shape, typestr):
         """Object exposing __cuda_array_interface__ (for torch.as_tensor)."""
         return _CudaArrayView(self, shape, typestr)

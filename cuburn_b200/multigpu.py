@@ -1,0 +1,113 @@
+"""
+Multi-GPU on one box: one process per GPU (torch.distributed, NCCL over NVLink).
+
+The reference's only multi-GPU mechanism is a job farm of OS processes fed over
+ssh pipes (distribute.py:131-248).  On an 8 x B200 box the same two ways of
+sharding are available in-process:
+
+  * stills: every GPU runs a disjoint share of the frame's samples with its own
+    RNG streams into a private float4 histogram; ``HistReducer`` sums them onto
+    the root with one NCCL reduce, and the root runs the filter chain.
+  * animations: whole frames are independent (points are re-seeded every frame),
+    so ``partition_frames`` deals frames round-robin and no collective is needed.
+
+torch is used only for process-group plumbing and the collective.
+"""
+import os
+
+import numpy as np
+
+
+def env_rank_world():
+    return (int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)),
+            int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', 0))))
+
+
+def init_process_group(backend=None):
+    """Join the process group described by the torchrun environment."""
+    import torch.distributed as dist
+    rank, world, local = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend is None:
+            import torch
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            import torch
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def sample_share(total_samples, rank, world, unit=65536):
+    """(first, count): the unit-aligned share of a frame's samples for `rank`."""
+    units = (int(total_samples) + unit - 1) // unit
+    lo, hi = units * rank // world, units * (rank + 1) // world
+    first = lo * unit
+    return first, max(min(hi * unit, int(total_samples)) - first, 0)
+
+
+def partition_frames(frames, rank, world):
+    """Round-robin frame assignment: frame k goes to rank k mod world."""
+    return [f for k, f in enumerate(frames) if k % world == rank]
+
+
+def seed_slice(rank, world, nstreams=262144):
+    """
+    Disjoint RNG streams per rank: the multiplier table is split into `world`
+    contiguous slices and each rank repeats its slice to fill its stream table
+    with independently drawn state/carry (different seeds per repeat).
+    """
+    per = nstreams // world
+    return rank * per, per
+
+
+def make_rank_seeds(rank, world, host_seed, nstreams=262144):
+    from . import mwc
+    mults = mwc.load_mults()
+    lo, per = seed_slice(rank, world, nstreams)
+    rs = np.random.RandomState((int(host_seed) * 1000003 + rank * 7919 + 1) % (2 ** 32))
+    seeds = np.empty((nstreams, 3), np.uint32)
+    seeds[:, 0] = np.resize(mults[lo:lo + per], nstreams)
+    seeds[:, 1] = rs.randint(1, 0x7fffffff, size=nstreams)
+    seeds[:, 2] = rs.randint(1, 0x7fffffff, size=nstreams)
+    return seeds
+
+
+class HistReducer(object):
+    """
+    ``RenderManager.hist_hook``: sums the per-GPU float4 histograms onto
+    ``root`` before the filter chain runs there.
+    """
+    def __init__(self, root=0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.root = torch, dist, root
+        self.reduce_ms = []
+
+    def tensor_view(self, buf, nfloats):
+        view = buf.view((int(nfloats),), '<f4')
+        return self.torch.as_tensor(view, device='cuda')
+
+    def __call__(self, fb, dim, stream):
+        if not self.dist.is_initialized() or self.dist.get_world_size() == 1:
+            return
+        stream.synchronize()          # iterate has finished writing d_front
+        t = self.tensor_view(fb.d_front, 4 * dim.ah * dim.astride)
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.dist.reduce(t, dst=self.root, op=self.dist.ReduceOp.SUM)
+        e1.record()
+        self.torch.cuda.current_stream().synchronize()
+        self.reduce_ms.append(e0.elapsed_time(e1))
+
+
+def reduce_host_hist(hist, root=0):
+    """gloo/CPU twin of the reduce, used by the world_size-2 CPU tests."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(hist))
+    dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
+    return t.numpy()

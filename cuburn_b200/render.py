@@ -201,15 +201,20 @@ class Renderer(object):
 
 class RenderManager(object):
     """Queues frames on the device (render.py:253-434)."""
-    def __init__(self, seed=None):
+    def __init__(self, seed=None, rank=0, world=1):
         N.ensure_init()
         self.fb = Framebuffers(seed=seed)
+        if world > 1:
+            # disjoint RNG streams per GPU (multigpu.make_rank_seeds)
+            from .multigpu import make_rank_seeds
+            N.memcpy_htod(self.fb.d_seeds, make_rank_seeds(rank, world, seed or 1,
+                                                           self.fb.nstreams))
         self.src_a, self.src_b = DevSrc(), DevSrc()
         self.info_a, self.info_b = DevInfo(), DevInfo()
         self.stream_a, self.stream_b = N.Stream(), N.Stream()
         self.filt_evt = self.copy_evt = None
         # share of the frame's samples this manager renders (multi-GPU stills)
-        self.sample_share = (0, 1)
+        self.sample_share = (rank, world)
         self.hist_hook = None
 
     # -- upload ----------------------------------------------------------------
