@@ -67,15 +67,21 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken in [t0, t1] (all samples if none fall inside)."""
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         time.sleep(0.15)
         self.proc.terminate()
+        inside = [ln for t, ln in self.lines
+                  if t0 is None or (t0 - 0.02 <= t <= t1 + 0.12)]
+        window = 'timed region'
+        if not inside:
+            inside, window = [ln for _, ln in self.lines], 'warm-up + timed region'
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -89,7 +95,7 @@ class ClockSampler(object):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None,
                     sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), window=window)
 
 
 def frame_setup(n_gpus, rank, seed=1):
@@ -154,7 +160,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -219,13 +225,13 @@ def main():
     # ---- device-resident timing ----------------------------------------------------
     rmgr._copy(rdr, gnm)
     evs = [[N.Event() for _ in range(4)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         device_step(*[N.Event() for _ in range(4)])
         l2_flush()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     step_ms, iter_ms = [], []
     for k in range(args.steps):
@@ -235,8 +241,9 @@ def main():
         barrier()
         step_ms.append(evs[k][3].time_since(evs[k][0]))
         iter_ms.append(evs[k][2].time_since(evs[k][1]))
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.perf_counter()
+    wall = wall1 - wall0
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     my_ms = float(np.sum(step_ms))
     if dist is not None:
         import torch
@@ -302,7 +309,8 @@ def main():
                'sample': '%d samples (1080p x 500 spp) of the same genome, chaos game only'
                          % n_cpu}
 
-    launches_per_step = 4 + 1 + 1 + 8 * 3 + 1 + 6 + 1     # fill, 3 interp, iter, yuv, bilateral, logscale, smearclip, convert
+    # 3 interp + fill + iter + unswizzle + yuv + 8 x 3 bilateral + logscale + 6 smearclip + convert
+    launches_per_step = 3 + 1 + 1 + 1 + 1 + 8 * 3 + 1 + 6 + 1
     line = {
         'metric': 'ifs_iterations_per_second', 'value': value, 'unit': 'iterations/s',
         'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,

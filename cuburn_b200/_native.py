@@ -57,7 +57,7 @@ class IterArgs(ctypes.Structure):
     _fields_ = [('hist', c_uint64), ('seeds', c_uint64), ('points', c_uint64),
                 ('params', c_uint64), ('palette', c_uint64), ('dim', Dims),
                 ('param_stride', c_int32), ('nts', c_int32),
-                ('pal_rows', c_int32), ('fuse_rounds', c_int32),
+                ('pal_rows', c_int32), ('fuse_rounds', c_int32), ('swizzle_bins', c_int32),
                 ('first_sample', c_uint64), ('nsamples', c_uint64),
                 ('total_samples', c_uint64)]
 
@@ -104,7 +104,9 @@ _SIGNATURES = {
                                       POINTER(c_int), POINTER(c_int)]),
     'cb_module_launch': (c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, POINTER(c_void_p), c_void_p]),
+    'cb_module_set_global': (c_int, [c_void_p, c_char_p, c_uint64, c_size_t, c_void_p]),
     'cb_iterate': (c_int, [c_void_p, POINTER(IterArgs), c_int, c_void_p]),
+    'cb_hist_unswizzle': (c_int, [c_uint64, c_uint64, c_int, POINTER(Dims), c_void_p]),
     'cb_yuv_to_rgb': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_den_blur': (c_int, [c_uint64, c_uint64, c_int, c_int, POINTER(c_float),
                             POINTER(Dims), c_void_p]),
@@ -114,6 +116,9 @@ _SIGNATURES = {
                              POINTER(Dims), c_void_p]),
     'cb_bilateral': (c_int, [c_uint64, c_uint64, c_uint64, c_int, c_int, c_float, c_float,
                              c_float, c_float, c_float, POINTER(Dims), c_void_p]),
+    'cb_bilateral_direction': (c_int, [c_uint64, c_uint64, c_uint64, c_int, c_int,
+                                       POINTER(c_float), c_float, c_float, c_float, c_float,
+                                       c_float, POINTER(Dims), c_void_p]),
     'cb_logscale': (c_int, [c_uint64, c_uint64, c_float, c_float, POINTER(Dims), c_void_p]),
     'cb_apply_gamma': (c_int, [c_uint64, c_uint64, c_float, POINTER(Dims), c_void_p]),
     'cb_haloclip': (c_int, [c_uint64, c_uint64, c_float, POINTER(Dims), c_void_p]),
@@ -372,6 +377,10 @@ class Module(object):
         check(lib().cb_module_kernel_info(self.handle, kernel.encode(), block_threads,
                                           byref(regs), byref(smem), byref(ctas)))
         return dict(num_regs=regs.value, static_smem=smem.value, ctas_per_sm=ctas.value)
+
+    def set_global(self, symbol, src, nbytes, stream=None):
+        check(lib().cb_module_set_global(self.handle, symbol.encode(), int(src), int(nbytes),
+                                         _sptr(stream)))
 
     def launch(self, kernel, grid, block, args, stream=None, dyn_smem=0):
         """args: list of ctypes values."""

@@ -49,6 +49,15 @@ __device__ __forceinline__ int clamp_idx(int x, int y, int w, int h) {
     int yi = blockIdx.y * 8 + threadIdx.y;                        \
     int gi = yi * dim.astride + xi
 
+// ---- histogram layout ---------------------------------------------------------------
+// Inverse of the slice-balancing accumulation layout (device/iter_kernel.cuh).
+__global__ void __launch_bounds__(256)
+k_hist_unswizzle(float4 *dst, const float4 *src, int swizzle_bins) {
+    unsigned int i = blockIdx.x * 256 + threadIdx.x;
+    unsigned int j = (i & 0xffff0000u) | ((i * 40503u) & 0xffffu);
+    dst[i] = src[(int)i < swizzle_bins ? j : i];
+}
+
 // ---- pointwise kernels: one float4 per thread, exact 1-D grid ---------------
 __global__ void __launch_bounds__(256)
 k_yuv_to_rgb(float4 *dst, const float4 *src) {
@@ -301,6 +310,109 @@ k_bilateral(float4 *dst, const float4 *src, const float *blur, int pattern,
     dst[gi] = make_float4(acc.x * rcp, acc.y * rcp, acc.z * rcp, acc.w * rcp);
 }
 
+// ---- restructured bilateral direction (same result, ~3x fewer SFU ops) -----------
+// The reference kernel spends ~8 MUFU operations per tap (powf of the tap density,
+// three exponentials, two reciprocals).  Everything that depends on one pixel only
+// is hoisted into two small prologue kernels, and the per-tap weight is evaluated
+// as ONE exp2 of a sum of log2-domain terms:
+//   factor = exp2( log2 spa[|r|] + log2e*cscale*cdiff + dscale*|cpow - pow_r|
+//                  - [r != 0] exp2(gspeed * grad) )
+// Prologue 1: aux[i].x = 7-tap blur of density (as den_blur), aux[i].y = w^dpow.
+// Prologue 2: side[i] = (1 / (two-octave blur + 1e-6), w^dpow)  (den_blur_1c, up = 1)
+__global__ void __launch_bounds__(256)
+k_bilat_prep1(float2 *aux, const float4 *src, int pattern, coefs7 k, float dpow,
+              cb_dims dim) {
+    PIX_XY();
+    float den = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        int2 o = shear_offset(pattern, (float)(i - 3));
+        den += src[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].w * k.c[i];
+    }
+    aux[gi] = make_float2(den, powf(src[gi].w, dpow));
+}
+
+__global__ void __launch_bounds__(256)
+k_bilat_prep2(float2 *side, const float2 *aux, int pattern, coefs7 k, cb_dims dim) {
+    PIX_XY();
+    float den = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        int2 o = shear_offset(pattern, (float)((i - 3) * 2));
+        den += aux[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].x * k.c[i];
+    }
+    side[gi] = make_float2(1.0f / (den + 1.0e-6f), aux[gi].y);
+}
+
+__global__ void __launch_bounds__(256)
+k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern,
+                 int radius, float sstd, float cstd, float dstd, float gspeed,
+                 cb_dims dim) {
+    PIX_XY();
+    __shared__ float lspa[32];
+    __shared__ int2 offs[36];
+    const float log2e = 1.44269502162933f;
+    if (threadIdx.y == 0) {
+        float df = (float)threadIdx.x;
+        lspa[threadIdx.x] = log2e * df * df / (-K_SQRT2 * sstd);
+    }
+    if (threadIdx.y == 1 && (int)threadIdx.x <= 2 * radius + 2)
+        offs[threadIdx.x] = shear_offset(pattern, (float)((int)threadIdx.x - radius - 1));
+    const int W = dim.astride, H = dim.aheight;
+    const float cscale2 = log2e / (-K_SQRT2 * 3.0f * cstd);
+    const float dscale = -0.5f / dstd;
+
+    float4 cen = src[gi];
+    float cpow = side[gi].y;
+    float cdrcp = 1.0f / (cen.w + 1.0e-6f);
+    cen.x *= cdrcp; cen.y *= cdrcp; cen.z *= cdrcp;
+    const bool cen_live = cen.w > 0.0f;
+
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float wsum = 0.0f;
+    __syncthreads();
+
+    int2 o = offs[0];
+    float4 pix = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
+    o = offs[1];
+    int ni = clamp_idx(xi + o.x, yi + o.y, W, H);
+    float4 next = src[ni];
+    float2 nside = side[ni];
+
+    for (int r = -radius; r <= radius; r++) {
+        float prev = pix.w;
+        pix = next;
+        float2 ps = nside;
+        o = offs[r + radius + 2];
+        ni = clamp_idx(xi + o.x, yi + o.y, W, H);
+        next = src[ni];
+        nside = side[ni];
+
+        float cdiff = 0.5f;
+        if (pix.w > 0.0f && cen_live) {
+            float pdrcp = 1.0f / pix.w;
+            float yd = pix.x * pdrcp - cen.x;
+            float ud = pix.y * pdrcp - cen.y;
+            float vd = pix.z * pdrcp - cen.z;
+            cdiff = yd * yd + ud * ud + vd * vd;
+        }
+        float e = lspa[abs(r)] + cscale2 * cdiff + dscale * fabsf(cpow - ps.y);
+        if (r != 0) {
+            float grad = (next.w - prev) * ps.x;
+            if (r < 0) grad = -grad;
+            e -= exp2f(gspeed * grad);
+        }
+        float f = exp2f(e);
+        wsum += f;
+        acc.x += f * pix.x;
+        acc.y += f * pix.y;
+        acc.z += f * pix.z;
+        acc.w += f * pix.w;
+    }
+    float rcp = 1.0f / (wsum + 1e-10f);
+    dst[gi] = make_float4(acc.x * rcp, acc.y * rcp, acc.z * rcp, acc.w * rcp);
+}
+
 // ---- C ABI -------------------------------------------------------------------
 static inline int nbins(const cb_dims *d) { return d->aheight * d->astride; }
 static inline dim3 grid2(const cb_dims *d) { return dim3(d->astride / 32, d->aheight / 8); }
@@ -319,6 +431,13 @@ static inline dim3 grid2(const cb_dims *d) { return dim3(d->astride / 32, d->ahe
     } while (0)
 
 extern "C" {
+
+int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins, const cb_dims *dim,
+                      cb_stream s) {
+    CB_REQUIRE(swizzle_bins >= 0 && swizzle_bins % 65536 == 0, "swizzle_bins must be a multiple of 65536");
+    CB_REQUIRE(dim && swizzle_bins <= dim->aheight * dim->astride, "swizzle_bins exceeds the grid");
+    POINTWISE(k_hist_unswizzle, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), swizzle_bins);
+}
 
 int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s) {
     POINTWISE(k_yuv_to_rgb, cb_ptr<float4>(dst), cb_ptr<const float4>(src));
@@ -415,6 +534,32 @@ int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern, int rad
     k_bilateral<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
         cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), cb_ptr<const float>(blur1),
         pattern, radius, sstd, cstd, dstd, dpow, gspeed, *dim);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+
+// One direction of the bilateral filter = den_blur + den_blur_1c + bilateral of the
+// reference recipe (cuburn/filters.py:80-94) with the per-pixel terms hoisted;
+// scratch4 is any float4-sized scratch buffer (holds two float2 planes).
+int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4, int pattern,
+                           int radius, const float coefs[7], float sstd, float cstd,
+                           float dstd, float dpow, float gspeed, const cb_dims *dim,
+                           cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(pattern >= 0 && pattern < 16 && coefs, "bad direction / coefs");
+    CB_REQUIRE(radius >= 0 && radius <= 16, "radius must be at most 16");
+    float2 *aux = cb_ptr<float2>(scratch4);
+    float2 *side = aux + (size_t)nbins(dim);
+    coefs7 k = load_coefs(coefs);
+    k_bilat_prep1<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+        aux, cb_ptr<const float4>(src4), pattern, k, dpow, *dim);
+    CB_LAUNCH_CHECK();
+    k_bilat_prep2<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
+    CB_LAUNCH_CHECK();
+    k_bilateral_fast<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+        cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
+        cstd, dstd, gspeed, *dim);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -29,6 +29,7 @@ struct DriverApi {
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int,
                                                           size_t) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *) = nullptr;
     bool ready = false;
 };
 
@@ -58,7 +59,8 @@ int ensure_driver() {
         !load_entry("cuFuncGetAttribute", &g_drv.FuncGetAttribute) ||
         !load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor",
                     &g_drv.OccupancyMaxActiveBlocksPerMultiprocessor) ||
-        !load_entry("cuGetErrorString", &g_drv.GetErrorString))
+        !load_entry("cuGetErrorString", &g_drv.GetErrorString) ||
+        !load_entry("cuModuleGetGlobal", &g_drv.ModuleGetGlobal))
         return CB_ERR_CUDA;
     g_drv.ready = true;
     return CB_OK;
@@ -192,10 +194,24 @@ int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,
     return CB_OK;
 }
 
+int cb_module_set_global(cb_module m, const char *symbol, cb_dptr src, size_t bytes,
+                         cb_stream s) {
+    CB_REQUIRE(m && symbol, "null argument");
+    int rc = module_load(m);
+    if (rc != CB_OK) return rc;
+    CUdeviceptr dst = 0;
+    size_t size = 0;
+    CB_DRV(g_drv.ModuleGetGlobal(&dst, &size, m->mod, symbol));
+    CB_REQUIRE(bytes <= size, "source larger than the module global");
+    CB_CUDA(cudaMemcpyAsync((void *)dst, (const void *)src, bytes,
+                            cudaMemcpyDeviceToDevice, cb_cs(s)));
+    return CB_OK;
+}
+
 int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas, cb_stream s) {
     CB_REQUIRE(m && args, "null argument");
     CB_REQUIRE(grid_ctas > 0, "grid_ctas must be positive");
-    CB_REQUIRE(args->first_sample % 65536ull == 0, "first_sample must be unit aligned");
+    CB_REQUIRE(args->first_sample % 16384ull == 0, "first_sample must be unit aligned");
     CB_REQUIRE(args->nts > 0 && args->pal_rows > 0, "bad temporal sample counts");
     cb_iter_args a = *args;
     void *kargs[1] = {&a};

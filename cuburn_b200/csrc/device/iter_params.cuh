@@ -1,0 +1,25 @@
+// Where the packed parameter block of the current temporal sample lives.
+// Included by the generated source after NSLOTS / PARAMS_CONST are defined and
+// before any function that reads P[slot].
+#pragma once
+
+#ifndef ITER_THREADS
+#define ITER_THREADS 256
+#endif
+#ifndef UNIT_ROUNDS
+#define UNIT_ROUNDS 64
+#endif
+#ifndef ITER_MIN_CTAS
+#define ITER_MIN_CTAS 8        // 32 registers, 64 warps / SM: measured fastest (profiles/r01_iter_variants.md)
+#endif
+
+#if PARAMS_CONST
+// Stills: one block for the whole launch.  Constant indices make every P[slot] a
+// constant-bank operand of the consuming instruction (no load, no register).
+__constant__ float c_params[NSLOTS > 0 ? NSLOTS : 1];
+#define P c_params
+#else
+// Motion blur: the CTA stages the block of its unit's temporal sample here.
+__shared__ float s_params[NSLOTS > 0 ? NSLOTS : 1];
+#define P s_params
+#endif

@@ -64,13 +64,10 @@ class Bilateral(Filter):
         for pattern in range(self.directions):
             # a "pixel" of spatial_std means a 1080p pixel (filters.py:74-76)
             sstd = params.spatial_std(tc) * dim.w / 1920.
-            # density blurred over two octaves along the sampling direction
-            N.check(L.cb_den_blur(fb.d_back.ptr, fb.d_front.ptr, pattern, 0, coefs,
-                                  N.byref(dim), s))
-            N.check(L.cb_den_blur_1c(fb.d_left.ptr, fb.d_back.ptr, pattern, 1, coefs,
-                                     N.byref(dim), s))
-            N.check(L.cb_bilateral(
-                fb.d_back.ptr, fb.d_front.ptr, fb.d_left.ptr, pattern, self.radius,
+            # den_blur -> den_blur_1c -> bilateral of the reference recipe
+            # (filters.py:80-94), fused into one restructured direction pass
+            N.check(L.cb_bilateral_direction(
+                fb.d_back.ptr, fb.d_front.ptr, fb.d_left.ptr, pattern, self.radius, coefs,
                 f32(sstd), f32(params.color_std(tc)), f32(params.density_std(tc)),
                 f32(params.density_pow(tc)), f32(params.gradient(tc)), N.byref(dim), s))
             fb.flip()

@@ -23,9 +23,9 @@ from .genome.util import palette_decode
 RenderedImage = namedtuple('RenderedImage', 'buf idx gpu_time')
 Dimensions = N.Dims
 
-# Samples one CTA processes between parameter reloads (256 threads x 256
-# rounds; the reference's block lifetime, iter.py:218).
-UNIT_SAMPLES = 65536
+# Samples one CTA processes per work unit (256 threads x 64 rounds); sample
+# ranges handed to cb_iterate are aligned to this.
+UNIT_SAMPLES = 16384
 ITER_THREADS = 256
 
 
@@ -154,15 +154,18 @@ class DevInfo(object):
 class Renderer(object):
     """
     A genome structure compiled for the device, plus its filter chain and
-    output module (render.py:225-251).  Modules are cached by generated source,
-    so genomes that share a structure share a module.
+    output module (render.py:225-251).  Two variants of the iterate module
+    exist per structure: parameters in __constant__ memory (stills: one block
+    per launch, every parameter a constant-bank operand) and parameters staged
+    in shared memory per temporal sample (motion blur).  Each is compiled on
+    first use and cached by generated source, so genomes that share a structure
+    share modules.
     """
-    MAX_MODREFS = 20
+    MAX_MODREFS = 40
     _modrefs = {}
 
     @classmethod
-    def compile(cls, gnm, arch=None, keep=False):
-        pk, src = itergen.mkiterlib(gnm)
+    def _module(cls, src):
         mod = cls._modrefs.get(src)
         if mod is None:
             names, hdrs = itergen.load_headers()
@@ -170,6 +173,12 @@ class Renderer(object):
             if len(cls._modrefs) > cls.MAX_MODREFS:
                 cls._modrefs.clear()
             cls._modrefs[src] = mod
+        return mod
+
+    @classmethod
+    def compile(cls, gnm, arch=None, keep=False, params_const=False):
+        pk, src = itergen.mkiterlib(gnm, params_const)
+        mod = cls._module(src)
         if keep:
             import os, tempfile
             base = os.path.join(tempfile.gettempdir(), 'iter_kern')
@@ -180,23 +189,35 @@ class Renderer(object):
         return pk, src, mod
 
     def __init__(self, gnm, gprof, keep=False, arch=None):
+        self._gnm_structure, self._keep = gnm, keep
         self.packer, self.lib, self.mod = self.compile(gnm, arch=arch, keep=keep)
+        self._mod_const = None
         self.filts = filters.create(gprof)
         self.out = output.get_output_for_profile(gprof)
-        self._grid = None
+        self._grid = {}
 
     @property
     def cubin(self):
         return self.mod.cubin
 
-    def grid_ctas(self, nstreams):
+    @property
+    def mod_const(self):
+        """The still variant (parameters in __constant__ memory), built on demand."""
+        if self._mod_const is None:
+            self._mod_const = self.compile(self._gnm_structure, keep=False,
+                                           params_const=True)[2]
+        return self._mod_const
+
+    def grid_ctas(self, nstreams, mod=None):
         """Persistent grid: every SM filled to the kernel's occupancy."""
-        if self._grid is None:
-            info = self.mod.kernel_info('cb_iter', ITER_THREADS)
+        mod = mod or self.mod
+        if id(mod) not in self._grid:
+            info = mod.kernel_info('cb_iter', ITER_THREADS)
             sms = N.device_info(N._initialised or 0)['sm_count']
             self.kernel_info = info
-            self._grid = max(1, min(info['ctas_per_sm'] * sms, nstreams // ITER_THREADS))
-        return self._grid
+            self._grid[id(mod)] = max(1, min(info['ctas_per_sm'] * sms,
+                                             nstreams // ITER_THREADS))
+        return self._grid[id(mod)]
 
 
 class RenderManager(object):
@@ -278,19 +299,35 @@ class RenderManager(object):
         n = min(hi * UNIT_SAMPLES, total) - first
         return total, first, max(n, 0)
 
+    # Accumulate in the slice-balancing layout (see device/iter_kernel.cuh) into the
+    # side buffer and unswizzle into d_front afterwards; False = accumulate straight
+    # into d_front in linear layout.
+    swizzle = True
+
     def _iter(self, rdr, gnm, gprof, dim, tc):
         s, info = self.stream_a, self.info_a
         nbins = dim.ah * dim.astride
-        N.fill32(self.fb.d_front, 4 * nbins, 0, s)
+        swz = (nbins // 65536) * 65536 if self.swizzle else 0
+        d_acc = self.fb.d_left if swz else self.fb.d_front
+        N.fill32(d_acc, 4 * nbins, 0, s)
         total, first, n = self.frame_samples(gprof, dim, tc)
+        # without motion blur all temporal samples are identical: use the variant
+        # that reads one parameter block from __constant__ memory
+        still = gprof.frame_width(tc) == 0
+        mod = rdr.mod_const if still else rdr.mod
+        if still:
+            mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
         args = N.IterArgs(
-            hist=self.fb.d_front.ptr, seeds=self.fb.d_seeds.ptr,
+            hist=int(d_acc), swizzle_bins=swz, seeds=self.fb.d_seeds.ptr,
             points=self.fb.d_points.ptr, params=info.d_params.ptr,
             palette=info.d_palette.ptr, dim=dim, param_stride=rdr.packer.param_stride,
             nts=info.ntemporal_samples, pal_rows=info.palette_height,
             fuse_rounds=info.fuse, first_sample=first, nsamples=n, total_samples=total)
-        N.check(N.lib().cb_iterate(rdr.mod.handle, N.byref(args),
-                                   rdr.grid_ctas(self.fb.nstreams), s.handle))
+        N.check(N.lib().cb_iterate(mod.handle, N.byref(args),
+                                   rdr.grid_ctas(self.fb.nstreams, mod), s.handle))
+        if swz:
+            N.check(N.lib().cb_hist_unswizzle(int(self.fb.d_front), int(d_acc), swz,
+                                              N.byref(dim), s.handle))
         self.last_iter_samples = n
 
     # -- frame -----------------------------------------------------------------------

@@ -129,6 +129,13 @@ int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,
                      int bx, int by, int bz, int dyn_smem, void **args,
                      cb_stream s);
 
+/* Stream-ordered device-to-device copy into a __constant__ / __device__ variable
+ * of the module (pycuda module.get_global + memcpy, render.py:290-293).  The
+ * still variant of the iterate module keeps its parameter block in the
+ * constant `c_params`. */
+int cb_module_set_global(cb_module m, const char *symbol, cb_dptr src,
+                         size_t bytes, cb_stream s);
+
 typedef struct {
     cb_dptr hist;        /* float4 [aheight][astride] accumulation buffer */
     cb_dptr seeds;       /* mwc_st [nstreams] */
@@ -141,14 +148,24 @@ typedef struct {
     int32_t pal_rows;    /* palette rows (64, render.py:202) */
     int32_t fuse_rounds; /* >0: reseed all points and run this many unrecorded
                             rounds first (iter.py:211-216) */
+    int32_t swizzle_bins; /* 0: hist is linear.  Otherwise a multiple of 65536:
+                            bins below it are stored in the slice-balancing
+                            layout that cb_hist_unswizzle undoes */
     uint64_t first_sample;   /* global index of the first sample of this call */
     uint64_t nsamples;       /* samples (recorded xform applications) to run */
     uint64_t total_samples;  /* samples of the whole frame, all calls/GPUs */
 } cb_iter_args;
 /* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
- * accumulated into hist.  grid_ctas persistent CTAs of 256 threads. */
+ * accumulated into hist.  grid_ctas persistent CTAs of 256 threads; work is
+ * split in units of 16384 samples and first_sample must be unit aligned. */
 int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas,
                cb_stream s);
+
+/* Undo the accumulation layout: dst[i] = src[swizzle(i)] for i < swizzle_bins,
+ * dst[i] = src[i] above; dst is the linear float4 [aheight][astride] histogram the
+ * filters consume (iter.py:395-406 semantics). */
+int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins,
+                      const cb_dims *dim, cb_stream s);
 
 /* ---- filters (code/filters.py; host recipes in cuburn/filters.py) -------- */
 int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s);
@@ -161,6 +178,14 @@ int cb_full_blur(cb_dptr dst4, cb_dptr src4, int pattern, int upsample,
 int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern,
                  int radius, float sstd, float cstd, float dstd, float dpow,
                  float gspeed, const cb_dims *dim, cb_stream s);
+/* One whole direction pass of the bilateral recipe (cuburn/filters.py:80-94:
+ * den_blur -> den_blur_1c(up=1) -> bilateral) in restructured form: per-pixel
+ * terms (w^dpow, 1/(blur+1e-6)) are hoisted into two prologue kernels and the tap
+ * weight is one exp2 of summed log2-domain terms.  scratch4: float4-sized. */
+int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4,
+                           int pattern, int radius, const float coefs[7],
+                           float sstd, float cstd, float dstd, float dpow,
+                           float gspeed, const cb_dims *dim, cb_stream s);
 int cb_logscale(cb_dptr dst4, cb_dptr src4, float k1, float k2,
                 const cb_dims *dim, cb_stream s);
 int cb_apply_gamma(cb_dptr dst1, cb_dptr src4, float gamma, const cb_dims *dim,

@@ -144,6 +144,44 @@ def test_bilateral_pass(native, built, pattern, kind):
     assert abs(got[..., 3].sum() / f[..., 3].sum() - 1) < 0.35
 
 
+@pytest.mark.parametrize('pattern', [0, 2, 5, 7])
+@pytest.mark.parametrize('kind', ['mixed', 'points', 'dense'])
+def test_bilateral_direction_fused(native, built, pattern, kind):
+    """The restructured direction pass (hoisted per-pixel terms, one exp2 per tap)
+    against the oracle's statement of the reference recipe."""
+    N = native
+    from oracle import filters_ref as F
+    from cuburn_b200.filters import gauss_coefs
+    dim, f = _field(6, kind)
+    src = upload_field(N, f)
+    scratch, d_out = N.DeviceBuffer(f.nbytes), N.DeviceBuffer(f.nbytes)
+    args = dict(sstd=6 * W / 1920. * 4, cstd=0.05, dstd=1.5, dpow=0.8, gspeed=4.0)
+    N.check(N.lib().cb_bilateral_direction(
+        d_out.ptr, src.ptr, scratch.ptr, pattern, 15, gauss_coefs(1),
+        np.float32(args['sstd']), np.float32(args['cstd']), np.float32(args['dstd']),
+        np.float32(args['dpow']), np.float32(args['gspeed']), N.byref(dim), None))
+    N.check(N.lib().cb_device_sync())
+    got = N.from_device(d_out, f.shape, np.float32)
+    want = F.bilateral_pass(f, pattern, 15, args['sstd'], args['cstd'], args['dstd'],
+                            args['dpow'], args['gspeed'])
+    assert np.all(np.isfinite(got)) and got.min() >= 0
+    scale = float(np.abs(want).max())
+    err = np.abs(got - want)
+    assert (err > 2e-3 * scale + 2e-3 * np.abs(want)).mean() < 1e-3, float(err.max())
+    # and against the unfused reference-shaped kernels on the device
+    d_a, d_b, d_ref = N.DeviceBuffer(f.nbytes // 4), N.DeviceBuffer(f.nbytes // 4), N.DeviceBuffer(f.nbytes)
+    L, c1 = N.lib(), gauss_coefs(1)
+    N.check(L.cb_den_blur(d_a.ptr, src.ptr, pattern, 0, c1, N.byref(dim), None))
+    N.check(L.cb_den_blur_1c(d_b.ptr, d_a.ptr, pattern, 1, c1, N.byref(dim), None))
+    N.check(L.cb_bilateral(d_ref.ptr, src.ptr, d_b.ptr, pattern, 15, np.float32(args['sstd']),
+                           np.float32(args['cstd']), np.float32(args['dstd']),
+                           np.float32(args['dpow']), np.float32(args['gspeed']),
+                           N.byref(dim), None))
+    N.check(L.cb_device_sync())
+    ref = N.from_device(d_ref, f.shape, np.float32)
+    assert (np.abs(got - ref) > 1e-3 * scale + 1e-3 * np.abs(ref)).mean() < 1e-3
+
+
 def test_pointwise_tonemap_kernels(native, built):
     N = native
     from oracle import filters_ref as F
