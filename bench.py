@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 CONFIG = dict(genome='G6F', width=1920, height=1080, spp=2000)
+# profiles/r01_final_cb_iter.md: 33.9 MB read + 0.1 MB written per launch (the first
+# touch of the histogram; 66 GB of atomic payload stays in L2)
+NCU_DRAM_BYTES_PER_LAUNCH = 33.96e6
 UNIT = 65536
 
 
@@ -96,6 +99,43 @@ class ClockSampler(object):
         return dict(sm_mhz=float(np.median(sm)) if sm else None,
                     sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
                     samples=len(sm), window=window)
+
+
+RED_SRC = r'''
+#include "mwc.cuh"
+// uniformly scattered 16-byte reductions into an L2-resident float4 grid, nothing else
+extern "C" __global__ void __launch_bounds__(256)
+red_peak(float4 *hist, mwc_st *seeds, unsigned int nbins, int rounds) {
+    int g = blockIdx.x * 256 + threadIdx.x;
+    mwc_st rng = seeds[g];
+    for (int r = 0; r < rounds; r++) {
+        unsigned int bin = __umulhi(mwc_next(rng), nbins);
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(hist + bin), "f"(0.25f), "f"(0.5f), "f"(0.75f), "f"(1.0f) : "memory");
+    }
+    seeds[g] = rng;
+}
+'''
+
+
+def measure_red_peak(N, hist_ptr, nbins, seeds_ptr, sms):
+    """Live microbenchmark: the scattered float4-reduction rate this GPU sustains into
+    a grid of the workload's size -- the roofline the accumulation runs against."""
+    import ctypes as C
+    from cuburn_b200.code import itergen
+    names, hdrs = itergen.load_headers()
+    mod = N.Module(RED_SRC, 'red_peak.cu', hdrs, names,
+                   ['--gpu-architecture=sm_100a', '--std=c++17'])
+    grid, rounds, best = sms * 4, 2048, 1e9
+    for _ in range(4):
+        e0, e1 = N.Event(), N.Event()
+        e0.record(None)
+        mod.launch('red_peak', (grid,), (256,),
+                   [C.c_uint64(hist_ptr), C.c_uint64(seeds_ptr), C.c_uint(nbins), C.c_int(rounds)])
+        e1.record(None)
+        e1.synchronize()
+        best = min(best, e1.time_since(e0))
+    return grid * 256 * rounds / (best * 1e-3)
 
 
 def frame_setup(n_gpus, rank, seed=1):
@@ -277,6 +317,9 @@ def main():
         + pk.nrows * 4 + pk.program_array().nbytes
     d2h = int(buf.nbytes)
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -294,6 +337,17 @@ def main():
                 'kernel_ms': iter_ms_mean,
                 'samples_per_second_kernel': mine / (iter_ms_mean * 1e-3)}
     nbins = dim.ah * dim.astride
+    red_peak = measure_red_peak(N, rmgr.fb.d_left.ptr, nbins, rmgr.fb.d_seeds.ptr,
+                                N.device_info(local)['sm_count'])
+    kernel_rate = mine / (iter_ms_mean * 1e-3)
+    roofline['atomic'] = {
+        'what': 'scattered red.global.add.v4.f32 into an L2-resident float4 grid of the '
+                'same size, measured in this run (the binding resource: L2 slice atomic rate)',
+        'achieved': kernel_rate, 'peak': red_peak, 'unit': 'reductions/s',
+        'frac': kernel_rate / red_peak}
+    # dram__bytes_read.sum + dram__bytes_write.sum of one cb_iter launch, from the
+    # committed ncu capture (profiles/); None until a capture exists for this kernel
+    roofline['traffic'] = NCU_DRAM_BYTES_PER_LAUNCH
     filt_ms = ms_per_step - iter_ms_mean
     roofline_filters = {'bound': 'hbm', 'stage': 'interp + filter chain + convert',
                         'algorithmic_bytes_per_bin': 804,
@@ -332,8 +386,8 @@ def main():
         'cpu_baseline': cpu,
         'wall_s_timed_region': wall,
     }
-    if reducer is not None and reducer.reduce_ms:
-        line['config']['nccl_reduce_ms'] = float(np.mean(reducer.reduce_ms[-args.steps:]))
+    if reducer is not None:
+        line['config']['nccl_reduce_ms'] = reducer.mean_reduce_ms(args.steps)
     print(json.dumps(line))
 
 

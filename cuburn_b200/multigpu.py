@@ -84,7 +84,7 @@ class HistReducer(object):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.root = torch, dist, root
-        self.reduce_ms = []
+        self._events = []
 
     def tensor_view(self, buf, nfloats):
         view = buf.view((int(nfloats),), '<f4')
@@ -93,15 +93,23 @@ class HistReducer(object):
     def __call__(self, fb, dim, stream):
         if not self.dist.is_initialized() or self.dist.get_world_size() == 1:
             return
-        stream.synchronize()          # iterate has finished writing d_front
+        torch = self.torch
         t = self.tensor_view(fb.d_front, 4 * dim.ah * dim.astride)
-        e0 = self.torch.cuda.Event(enable_timing=True)
-        e1 = self.torch.cuda.Event(enable_timing=True)
-        e0.record()
-        self.dist.reduce(t, dst=self.root, op=self.dist.ReduceOp.SUM)
-        e1.record()
-        self.torch.cuda.current_stream().synchronize()
-        self.reduce_ms.append(e0.elapsed_time(e1))
+        # Run the collective in stream order on the renderer's own stream (wrapped
+        # as a torch ExternalStream): no host synchronisation on either side.
+        ext = torch.cuda.ExternalStream(stream.handle.value)
+        with torch.cuda.stream(ext):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.dist.reduce(t, dst=self.root, op=self.dist.ReduceOp.SUM)
+            e1.record()
+        self._events.append((e0, e1))
+
+    def mean_reduce_ms(self, last=None):
+        """Device time of the recorded reduces (call after a synchronize)."""
+        evs = self._events[-last:] if last else self._events
+        return float(np.mean([a.elapsed_time(b) for a, b in evs])) if evs else None
 
 
 def reduce_host_hist(hist, root=0):
