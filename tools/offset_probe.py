@@ -14,7 +14,7 @@ w, h, spp = 1920, 1080, 1000
 gnm = samples.GENOMES[gname]()
 gprof = profile.wrap(dict(width=w, height=h, spp=spp, frame_width=0, start=1, end=2), gnm)
 tc = profile.enumerate_times(gprof)[0][1][0]
-rmgr = render.RenderManager(seed=1); rmgr.swizzle = os.environ.get('SWZ', '1') == '1'
+rmgr = render.RenderManager(seed=1); rmgr.swizzle = {'1': True, '0': False}.get(os.environ.get('SWZ', 'auto'), 'auto')
 rdr = render.Renderer(gnm, gprof)
 dim = rmgr.fb.set_dim(w, h)
 rmgr._copy(rdr, gnm)
