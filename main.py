@@ -6,9 +6,8 @@ Render fractal flames on a B200 -- the reference's command line
     python main.py FLAME.json -P 1080p --still -o out/
     python main.py sample:G6F -P 1080p --still          (built-in sample genomes)
 
-Genomes are 'animation' JSON documents (cuburn/genome/specs.py:104-105).  flam3
-XML conversion and node/edge blending (cuburn/genome/convert.py, blend.py) are
-the next rows of the build and are not available yet.
+Accepts what the reference accepts: flam3 XML (.flam3 / .flame), cuburn JSON nodes,
+edges and animations, by file name or by ID inside a genome DB (-d).
 """
 import argparse
 import json
@@ -21,25 +20,19 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from cuburn_b200 import profile  # noqa: E402
 
 
-def load_anim(path):
-    if path.startswith('sample:'):
+def load_anim(args):
+    """``(animation dict, basename)`` through the genome DB (main.py:29-30)."""
+    if args.flame.startswith('sample:'):
         from cuburn_b200 import samples
-        name = path.split(':', 1)[1]
+        name = args.flame.split(':', 1)[1]
         return samples.GENOMES[name](), name
-    with open(path) as fp:
-        text = fp.read()
-    if text.lstrip().startswith('<'):
-        raise SystemExit('flam3 XML input needs the genome conversion layer, which '
-                         'is not built yet; convert to cuburn JSON first')
-    gnm = json.loads(text)
-    if gnm.get('type') != 'animation':
-        raise SystemExit("only 'animation' genomes can be rendered (got %r); "
-                         'blend nodes/edges first' % gnm.get('type'))
-    return gnm, os.path.basename(path).rsplit('.', 1)[0]
+    from cuburn_b200.genome import db
+    gdb = db.connect(args.genomedb)
+    return gdb.get_anim(args.flame, args.half)
 
 
 def main(args, prof):
-    gnm, basename = load_anim(args.flame)
+    gnm, basename = load_anim(args)
     if getattr(args, 'print'):
         from cuburn_b200.genome.util import json_encode
         sys.stdout.write(json_encode(gnm))
@@ -107,7 +100,7 @@ if __name__ == '__main__':
     parser.add_argument('flame', metavar='ID', type=str, nargs='?',
                         help='Filename of the genome to render (or sample:NAME)')
     parser.add_argument('-d', '--genomedb', metavar='PATH', type=str, default='.',
-                        help='Path to genome database (accepted for compatibility)')
+                        help="Path to genome database (file or directory, default '.')")
     parser.add_argument('--raw', metavar='PATH', type=str, dest='rawfn',
                         help='Target file for raw buffer, to enable previews.')
     parser.add_argument('--half', action='store_true',
