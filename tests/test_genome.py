@@ -127,3 +127,49 @@ def test_schema_matches_reference():
             assert a[:len(a) - 1] == b[:len(b) - 1] or a == b, path
     for top in ('anim', 'node', 'edge', 'profile'):
         same(rs[top], getattr(specs, top), top)
+
+
+def test_reference_generated_host_vectors(built):
+    """
+    tests/golden/host_golden.json comes from executing the reference's use.py,
+    profile.py and mwc.make_seeds (tests/golden/make_host_golden.py).
+    """
+    import json
+    import os
+    from cuburn_b200 import profile, mwc, filters
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                           'host_golden.json')) as fp:
+        gold = json.load(fp)
+    for c in gold['splines']:
+        se = use.SplineEval(c['value'], c['scale'])
+        assert np.allclose(se.knots, np.array(c['knots']), rtol=0, atol=0)
+        for t, v, dv in c['at']:
+            assert abs(se(t) - v) <= 1e-9 * max(1, abs(v))
+            assert abs(se(t, 1) - dv) <= 1e-7 * max(1, abs(dv))
+    for c in gold['profile']:
+        args = profile.add_args().parse_args(c['argv'])
+        name, p = profile.get_from_args(args)
+        assert name == c['name'] and p == c['profile']
+        gprof = profile.wrap(dict(p), {'type': 'animation', 'camera': {'spp': 1.5},
+                                       'time': {'duration': 2, 'frame_width': [1.0, 0.5]}})
+        times = profile.enumerate_times(gprof)
+        assert len(times) == c['ntimes']
+        for (i, t), (gi, gt) in zip(times, c['times']):
+            assert i == gi and np.allclose(list(t), gt, rtol=0, atol=1e-15)
+        assert abs(gprof.spp(0.5) - c['spp']) < 1e-9
+        assert abs(gprof.frame_width(0.25) - c['frame_width']) < 1e-12
+        assert gprof.duration == c['duration'] and [gprof.width, gprof.height] == c['size']
+    s = gold['seeds']
+    seeds = mwc.make_seeds(s['n'], host_seed=s['host_seed'])
+    assert seeds[:4].tolist() == s['first'] and seeds[-2:].tolist() == s['last']
+    assert [int(np.bitwise_xor.reduce(seeds[:, k])) for k in range(3)] == s['xor']
+    for stdev, coefs in gold['filters']['gauss'].items():
+        assert [float(x) for x in filters.gauss_coefs(float(stdev))] == coefs
+
+    class P(object):
+        def __init__(self, g, t):
+            self.gamma = lambda tc: g
+            self.gamma_threshold = lambda tc: t
+    for gamma, thr, gam, lin, lingam in gold['filters']['lingam']:
+        got = filters.calc_lingam(P(gamma, thr), 0.5)
+        assert [float(x) for x in got] == [gam, lin, lingam]
