@@ -5,12 +5,21 @@ A CPU restatement of the reference renderer's hot path (stevenrobertson/cuburn),
 used only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  Nothing under cuburn_b200/ imports this package.
 
-Parity status: the reference cannot be executed here (Python 2 + PyCUDA +
-CUDA-4-era texture references).  The oracle is pinned
-against the only known-answer material the reference holds for this path -- the
-MWC recurrence model (code/mwc.py:90-129), the multiplier table
-(code/primes.bin, regenerated and compared byte for byte), the pixel-format
-assertions (code/tests/test_output.py) and the profile-time tests -- and is
-otherwise a line-by-line restatement of the cited sources: interpolation,
-palette, iterate, variations, filters: **parity unpinned by reference vectors**.
+Parity status.  The reference as a whole cannot be executed here (Python 2 +
+PyCUDA + CUDA-4-era texture references), but large parts of
+it can, and the oracle is pinned against every one of them:
+
+  * the reference's own DEVICE code compiled for the CPU from the sources in place
+    (oracle/build_ref.py -> oracle/_ref/): all 95 variation bodies, catmull_rom /
+    catmull_rom_mag with the knot search, the YUV helpers -- tests/test_reference_code.py
+  * the reference's own HOST code executed under Python 3 (tests/golden/make_*_golden.py):
+    SplineEval, profile enumeration, make_seeds, flam3 conversion and blending
+  * the MWC recurrence model (code/mwc.py:90-129) and the multiplier table
+    (code/primes.bin, regenerated and compared byte for byte)
+  * the pixel-format assertions of code/tests/test_output.py and the profile tests
+
+Not covered by reference-generated vectors (templated kernels with inline PTX and
+texture references that cannot be built here): the iterate kernel's control flow,
+the palette kernel, the filter kernels and rgba8/16 + yuv444p12 output.  For those
+the oracle is a line-by-line restatement of the cited sources: **parity unpinned**.
 """

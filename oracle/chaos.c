@@ -580,6 +580,18 @@ static void variation(int id, const float *a, float w, float *ptx, float *pty,
     }
 }
 
+/* One variation on arrays of points, for checking this file against the
+ * reference's own variation bodies compiled for the CPU (oracle/build_ref.py). */
+void oracle_variation(int id, const float *args, float w, float *txs, float *tys,
+                      float *oxs, float *oys, uint32_t *seeds, int n) {
+    for (int i = 0; i < n; i++) {
+        mwc_t s = {seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]};
+        variation(id, args, w, &txs[i], &tys[i], &oxs[i], &oys[i], &s);
+        seeds[3 * i + 1] = s.state;
+        seeds[3 * i + 2] = s.carry;
+    }
+}
+
 /* apply_xf (code/iter.py:121-149) */
 static void apply_xform(const float *xf, float *x, float *y, float *color, mwc_t *rng) {
     const float *p = xf + XF_PRE;

@@ -507,6 +507,22 @@ def mwc_sums(seeds, rounds):
     return sums, seeds
 
 
+def variation(var_id, args, w, txs, tys, seeds):
+    """One variation (flam3 number) on arrays: returns (tx, ty, ox, oy, seeds)."""
+    txs, tys = np.array(txs, f32), np.array(tys, f32)
+    oxs, oys = np.zeros_like(txs), np.zeros_like(txs)
+    seeds = np.array(seeds, np.uint32)
+    a = np.zeros(12, f32)
+    a[:len(args)] = args
+    chaos_lib().oracle_variation(ctypes.c_int(var_id), _p(a), ctypes.c_float(w), _p(txs), _p(tys),
+                                 _p(oxs), _p(oys), _p(seeds), ctypes.c_int(txs.size))
+    return txs, tys, oxs, oys, seeds
+
+
+def var_number(name):
+    return _VAR_NUM[name]
+
+
 def apply_xform(xf_record, xs, ys, cs, seeds):
     xs, ys, cs = (np.ascontiguousarray(a, f32).copy() for a in (xs, ys, cs))
     seeds = np.ascontiguousarray(seeds, np.uint32).copy()
