@@ -11,15 +11,19 @@ it can, and the oracle is pinned against every one of them:
 
   * the reference's own DEVICE code compiled for the CPU from the sources in place
     (oracle/build_ref.py -> oracle/_ref/): all 95 variation bodies, catmull_rom /
-    catmull_rom_mag with the knot search, the YUV helpers -- tests/test_reference_code.py
+    catmull_rom_mag with the knot search, the camera / affine / variation precalc
+    hunks, the YUV helpers, interp_palette_flat, every filter kernel (run through a
+    serial CUDA shim with clamp-to-edge textures) and all six f32_to_* pixel-format
+    kernels -- tests/test_reference_code.py
   * the reference's own HOST code executed under Python 3 (tests/golden/make_*_golden.py):
     SplineEval, profile enumeration, make_seeds, flam3 conversion and blending
   * the MWC recurrence model (code/mwc.py:90-129) and the multiplier table
     (code/primes.bin, regenerated and compared byte for byte)
   * the pixel-format assertions of code/tests/test_output.py and the profile tests
 
-Not covered by reference-generated vectors (templated kernels with inline PTX and
-texture references that cannot be built here): the iterate kernel's control flow,
-the palette kernel, the filter kernels and rgba8/16 + yuv444p12 output.  For those
-the oracle is a line-by-line restatement of the cited sources: **parity unpinned**.
+Not covered by reference-generated vectors: the `iter` kernel's own control flow
+(weighted xform choice, inter-warp shuffle, binning through `cvt.rni`, packed-u64
+accumulation and `flush_atom` -- tempita control flow plus inline PTX) and
+`precalc_densities`.  For those the oracle is a line-by-line restatement of the cited
+sources: **parity unpinned** for that part only.
 """

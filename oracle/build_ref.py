@@ -35,11 +35,62 @@ def available():
 
 
 class _Template(object):
+    """Stand-in for tempita.Template: keeps the raw text; renders ``{{expr}}``
+    placeholders (no control flow) by evaluating them against the arguments."""
     def __init__(self, content, name=None, namespace=None, **kw):
-        self.content, self.name = content, name
+        self.content, self.name, self.namespace = content, name, namespace or {}
 
     def substitute(self, *a, **kw):
-        raise RuntimeError('templates are not rendered here')
+        ns = dict(self.namespace)
+        for d in a:
+            if isinstance(d, dict):
+                ns.update(d)
+        ns.update(kw)
+        if '{{for' in self.content or '{{if' in self.content or '{{py:' in self.content:
+            raise RuntimeError('template %s uses control flow' % self.name)
+        return re.sub(r'\{\{(.*?)\}\}', lambda m: str(eval(m.group(1), ns)), self.content)
+
+
+class _FakeNode(object):
+    """Stands in for the packer views the precalc templates are rendered against:
+    reading ``node.a.b`` yields the C identifier ``in_<prefix>_a_b``, ``_set('x')``
+    yields ``out_<prefix>_x``; both are recorded in order of first use."""
+    def __init__(self, prefix, reg=None, code=None):
+        self._prefix = prefix
+        self._reg = reg if reg is not None else {'in': [], 'out': []}
+        self._codes = code if code is not None else []
+
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return _FakeNode(self._prefix + '_' + name, self._reg, self._codes)
+
+    def _precalc(self):
+        return self
+
+    def _set(self, name):
+        ident = 'out_%s_%s' % (self._prefix, name)
+        if ident not in self._reg['out']:
+            self._reg['out'].append(ident)
+        return ident
+
+    def _code(self, code):
+        self._codes.append(code)
+
+    def __str__(self):
+        ident = 'in_' + self._prefix
+        if ident not in self._reg['in']:
+            self._reg['in'].append(ident)
+        return ident
+
+
+def _precalc_function(cname, codes, reg, extra_args=''):
+    """Wrap rendered precalc hunks into  void cname(const float *in, float *out, ...)."""
+    body = ''.join('    float %s = in[%d];\n' % (n, i) for i, n in enumerate(reg['in']))
+    body += ''.join('    float %s = 0.0f;\n' % n for n in reg['out'])
+    body += ''.join('    {\n%s\n    }\n' % c for c in codes)
+    body += ''.join('    out[%d] = %s;\n' % (i, n) for i, n in enumerate(reg['out']))
+    return 'extern "C" void %s(const float *in, float *out%s) {\n%s}\n' % (cname, extra_args, body)
 
 
 def _exec_reference(fname, stubs):
@@ -93,6 +144,112 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r 
 #define __noinline__
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline float max(float a, float b) { return a > b ? a : b; }
+'''
+
+
+CUDA_SHIM = r'''
+struct uint2 { uint32_t x, y; };
+struct float2 { float x, y; };
+struct uchar3 { unsigned char x, y, z; };
+struct uchar4 { unsigned char x, y, z, w; };
+struct ushort3 { unsigned short x, y, z; };
+struct ushort4 { unsigned short x, y, z, w; };
+static inline uchar3 make_uchar3(float x, float y, float z) { uchar3 r = {(unsigned char)x, (unsigned char)y, (unsigned char)z}; return r; }
+static inline uchar4 make_uchar4(float x, float y, float z, float w) { uchar4 r = {(unsigned char)x, (unsigned char)y, (unsigned char)z, (unsigned char)w}; return r; }
+static inline ushort3 make_ushort3(float x, float y, float z) { ushort3 r = {(unsigned short)x, (unsigned short)y, (unsigned short)z}; return r; }
+static inline ushort4 make_ushort4(float x, float y, float z, float w) { ushort4 r = {(unsigned short)x, (unsigned short)y, (unsigned short)z, (unsigned short)w}; return r; }
+struct idx3 { int x, y, z; };
+static idx3 threadIdx, blockIdx, blockDim, gridDim;
+#define __global__
+#define __shared__ static
+#define __constant__ static
+#define __restrict__
+static inline void __syncthreads() {}
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline void scale_float4(float4 &pix, float scale) { pix.x *= scale; pix.y *= scale; pix.z *= scale; pix.w *= scale; }
+// point-sampled 2-D texture reference with unnormalised coordinates: clamp to edge
+enum { cudaTextureType2D = 2, cudaSurfaceType2D = 2 };
+template <typename T, int D> struct texture { const T *ptr; int w, h; };
+template <typename T> static inline T tex2D(texture<T, cudaTextureType2D> &t, float x, float y) {
+    int xi = (int)floorf(x), yi = (int)floorf(y);
+    xi = xi < 0 ? 0 : (xi >= t.w ? t.w - 1 : xi);
+    yi = yi < 0 ? 0 : (yi >= t.h ? t.h - 1 : yi);
+    return t.ptr[yi * t.w + xi];
+}
+template <typename T, int D> struct surface { uint2 *ptr; int wbytes; };
+static inline void surf2Dwrite(uint2 v, surface<void, cudaSurfaceType2D> &s, int xbytes, int y) {
+    s.ptr[(y * s.wbytes + xbytes) / 8] = v;
+}
+// ring buffer slot claim (code/util.py:329-335) for a serial emulation in which
+// thread 0 of a block runs first
+typedef struct { uint32_t head; uint32_t tail; } ringbuf;
+static uint32_t rb_idx;
+static uint32_t rb_incr(uint32_t &rb_base, int tidx) {
+    if (threadIdx.y == 0 && threadIdx.x == 0) rb_idx = 256 * ((rb_base++) & 1023);
+    return rb_idx + tidx;
+}
+// run a kernel body for every thread of a (bx, by) grid of (tx, ty) blocks, serially
+template <typename F> static void run_grid(int gx, int gy, int tx, int ty, int passes, F f) {
+    gridDim.x = gx; gridDim.y = gy; gridDim.z = 1; blockDim.x = tx; blockDim.y = ty; blockDim.z = 1;
+    for (int by = 0; by < gy; by++) for (int bx = 0; bx < gx; bx++)
+        for (int pass = 0; pass < passes; pass++)        // pass 0 fills __shared__ tables
+            for (int y = 0; y < ty; y++) for (int x = 0; x < tx; x++) {
+                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = 0;
+                threadIdx.x = x; threadIdx.y = y; threadIdx.z = 0;
+                f();
+            }
+}
+'''
+
+KERNEL_ENTRIES = r'''
+static void bind4(const float *p, int w, int h) { chan4_src.ptr = (const float4 *)p; chan4_src.w = w; chan4_src.h = h; }
+static void bind1(const float *p, int w, int h) { chan1_src.ptr = p; chan1_src.w = w; chan1_src.h = h; }
+#define GRID2(W, H, PASSES, CALL) run_grid((W) / 32, (H) / 8, 32, 8, PASSES, [&]() { CALL; })
+extern "C" {
+void ref_set_gauss(const float *c) { for (int i = 0; i < 7; i++) gauss_coefs[i] = c[i]; }
+void ref_yuv_to_rgb(float *dst, const float *src, int w, int h) { GRID2(w, h, 1, yuv_to_rgb((float4 *)dst, (const float4 *)src)); }
+void ref_logscale(float *dst, const float *src, float k1, float k2, int w, int h) { GRID2(w, h, 1, logscale((float4 *)dst, (const float4 *)src, k1, k2)); }
+void ref_logencode(float *dst, const float *src, float degamma, int w, int h) { GRID2(w, h, 1, logencode((float4 *)dst, (const float4 *)src, degamma)); }
+void ref_den_blur(float *dst, const float *src4, int pattern, int up, int w, int h) { bind4(src4, w, h); GRID2(w, h, 1, den_blur(dst, pattern, up)); }
+void ref_den_blur_1c(float *dst, const float *src1, int pattern, int up, int w, int h) { bind1(src1, w, h); GRID2(w, h, 1, den_blur_1c(dst, pattern, up)); }
+void ref_full_blur(float *dst, const float *src4, int pattern, int up, int w, int h) { bind4(src4, w, h); GRID2(w, h, 1, full_blur((float4 *)dst, pattern, up)); }
+void ref_bilateral(float *dst, const float *src4, const float *blur1, int pattern, int radius, float sstd, float cstd,
+                   float dstd, float dpow, float gspeed, int w, int h) {
+    bind4(src4, w, h); bind1(blur1, w, h);
+    GRID2(w, h, 2, bilateral((float4 *)dst, pattern, radius, sstd, cstd, dstd, dpow, gspeed));
+}
+void ref_apply_gamma(float *dst, float *src4, float gamma, int w, int h) { GRID2(w, h, 1, apply_gamma(dst, (float4 *)src4, gamma)); }
+void ref_haloclip(float *pix, const float *den, float gm1, int w, int h) { GRID2(w, h, 1, haloclip((float4 *)pix, den, gm1)); }
+void ref_apply_gamma_full_hi(float *dst, float *src, float gm1, int w, int h) { GRID2(w, h, 1, apply_gamma_full_hi((float4 *)dst, (float4 *)src, gm1)); }
+void ref_smearclip(float *pix, const float *smear, float gm1, float lin, float lingam, int w, int h) { GRID2(w, h, 1, smearclip((float4 *)pix, (const float4 *)smear, gm1, lin, lingam)); }
+void ref_plainclip(float *pix, float gm1, float lin, float lingam, float brightness, int w, int h) { GRID2(w, h, 1, plainclip((float4 *)pix, gm1, lin, lingam, brightness)); }
+void ref_colorclip(float *pix, float vib, float hipow, float gamma, float lin, float lingam, int w, int h) { GRID2(w, h, 1, colorclip((float4 *)pix, vib, hipow, gamma, lin, lingam)); }
+
+// pixel formats: launchC geometry (cuburn/output.py:21-26); rctxs must hold 1024*256 streams
+#define OUT_KERNEL(NAME, T) \
+void ref_##NAME(void *dst, const float *src, int gutter, int w, int sstride, int h, uint32_t *seeds) { \
+    ringbuf rb = {0, 0}; \
+    run_grid((w + 31) / 32, (h + 7) / 8, 32, 8, 1, [&]() { \
+        if ((int)(blockIdx.x * blockDim.x + threadIdx.x) >= w || (int)(blockIdx.y * blockDim.y + threadIdx.y) >= h) { \
+            /* keep the slot bookkeeping of out-of-frame threads without touching memory */ \
+            int tid = blockDim.x * threadIdx.y + threadIdx.x; rb_incr(rb.head, tid); rb_incr(rb.tail, tid); return; } \
+        NAME((T *)dst, (const float4 *)src, gutter, w, sstride, h, &rb, (mwc_st *)seeds); }); }
+OUT_KERNEL(f32_to_rgba_u8, uchar4)
+OUT_KERNEL(f32_to_rgba_u16, ushort4)
+OUT_KERNEL(f32_to_yuv444p, char)
+OUT_KERNEL(f32_to_yuv444p10, uint16_t)
+OUT_KERNEL(f32_to_yuv420p10, uint16_t)
+OUT_KERNEL(f32_to_yuv444p12, uint16_t)
+
+// palette: 64 blocks x 256 threads (cuburn/render.py:295-301)
+void ref_interp_palette(uint32_t *out /* [rows][256][2] */, uint32_t *seeds, const float *times,
+                        const float *sources, float tstart, float tstep, int rows) {
+    ringbuf rb = {0, 0};
+    flatpal.ptr = (uint2 *)out; flatpal.wbytes = 256 * 8;
+    run_grid(rows, 1, 256, 1, 1, [&]() {
+        interp_palette_flat(&rb, (mwc_st *)seeds, times, (const float4 *)sources, tstart, tstep); });
+}
+}
 '''
 
 
@@ -169,6 +326,37 @@ extern "C" void ref_catmull_rom(const float *times, const float *knots, const fl
         out[i] = mag ? catmull_rom_mag(times, knots, ts[i]) : catmull_rom(times, knots, ts[i]);
 }
 ''')
+    # precalc hunks: camera and affine (code/iter.py:56-95) and the variation
+    # precalcs (code/variations.py), rendered against fake packer views
+    mwc_stub = types.SimpleNamespace(mwclib=None)
+    cuburn_pkg = types.ModuleType('cuburn')
+    cuburn_pkg.genome = types.ModuleType('cuburn.genome')
+    cuburn_pkg.genome.specs = types.ModuleType('cuburn.genome.specs')
+    itermod = _exec_reference('iter.py', {
+        'variations': varmod, 'interp': interp, 'util': util_stub, 'mwc': mwc_stub,
+        'cuburn': cuburn_pkg, 'cuburn.genome': cuburn_pkg.genome,
+        'cuburn.genome.specs': cuburn_pkg.genome.specs})
+    meta['precalc'] = {}
+    parts.append('typedef struct { uint32_t width, height, awidth, aheight, astride; } acc_size_t;\n'
+                 'static acc_size_t acc_size;')
+    cam = _FakeNode('cam')
+    itermod.precalc_camera(cam)
+    parts.append(_precalc_function('ref_precalc_camera_', cam._codes, cam._reg))
+    parts.append('extern "C" void ref_precalc_camera(const float *in, float *out, int width, '
+                 'int awidth, int aheight) {\n    acc_size.width = width; acc_size.awidth = awidth; '
+                 'acc_size.aheight = aheight;\n    ref_precalc_camera_(in, out);\n}')
+    meta['precalc']['camera'] = cam._reg
+    px = _FakeNode('px')
+    itermod.precalc_xf_affine(px)
+    parts.append(_precalc_function('ref_precalc_affine', px._codes, px._reg))
+    meta['precalc']['affine'] = px._reg
+    for vname in ('waves', 'perspective', 'julian', 'juliascope', 'curve'):
+        reg, codes = {'in': [], 'out': []}, []
+        pvn, pxn = _FakeNode('pv', reg, codes), _FakeNode('px', reg, codes)
+        varmod.var_code[vname].namespace['precalc_fun'](pvn, pxn)
+        parts.append(_precalc_function('ref_precalc_' + vname, codes, reg))
+        meta['precalc'][vname] = reg
+
     # colour helpers (code/color.py:12-42)
     color = _exec_reference('color.py', {'util': util_stub, 'numpy': __import__('numpy')})
     parts.append(color.yuvlib.decls)
@@ -187,6 +375,29 @@ extern "C" void ref_yuvo2rgb(float *pix, int n) {
     }
 }
 ''')
+    # ---- kernels: filters, pixel formats, palette --------------------------------
+    parts.append(CUDA_SHIM)
+    usrc = open(REF + 'util.py').read()
+    parts.append(usrc[usrc.index('#define GET_IDX_2'):usrc.index('""", defs=r\'\'\'\n__device__ uint32_t gtid')])
+    filt = _exec_reference('filters.py', {'util': util_stub, 'color': color})
+    shear = filt.texshearlib.defs
+    # the only inline PTX in the filter code: round-to-nearest-even of i and j
+    a0 = shear.index('asm("{')
+    a1 = shear.index(': "+f"(i), "+f"(j));') + len(': "+f"(i), "+f"(j));')
+    shear = shear[:a0] + 'i = nearbyintf(i); j = nearbyintf(j);' + shear[a1:]
+    parts.append('extern "C" {')
+    parts.append(filt.denblurlib.decls)
+    parts.append(shear)
+    parts.append('}')
+    for lib_ in (filt.logscalelib, filt.yuvfilterlib, filt.logencodelib, filt.denblurlib,
+                 filt.fullblurlib, filt.bilaterallib, filt.halocliplib, filt.smearcliplib,
+                 filt.plaincliplib, filt.colorcliplib):
+        parts.append(lib_.defs)
+    outmod = _exec_reference('output.py', {'util': util_stub, 'mwc': mwc_stub})
+    parts.append(outmod.pixfmtlib.defs)
+    parts.append(interp.palintlib.decls)
+    parts.append(interp.palintlib.defs)
+    parts.append(KERNEL_ENTRIES)
     return '\n'.join(parts), meta
 
 
@@ -279,6 +490,78 @@ def ref_yuvo2rgb(pix):
     pix = np.array(pix, np.float32)
     lib().ref_yuvo2rgb(pix.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(pix.shape[0]))
     return pix
+
+
+def _fp(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def ref_precalc(kind, inputs, width=0, awidth=0, aheight=0):
+    """Run a reference precalc hunk; returns {output identifier: value}."""
+    import ctypes
+    import numpy as np
+    reg = meta()['precalc'][kind]
+    inp = np.array([inputs[n] for n in reg['in']], np.float32)
+    out = np.zeros(len(reg['out']), np.float32)
+    if kind == 'camera':
+        lib().ref_precalc_camera(_fp(inp), _fp(out), ctypes.c_int(width), ctypes.c_int(awidth),
+                                 ctypes.c_int(aheight))
+    else:
+        getattr(lib(), 'ref_precalc_' + kind)(_fp(inp), _fp(out))
+    return dict(zip(reg['out'], out))
+
+
+def ref_filter(name, *arrays_and_scalars, shape=None):
+    """Call ref_<name>(array..., scalar..., astride, aheight); arrays are float32 and
+    modified in place where the reference kernel writes them."""
+    import ctypes
+    import numpy as np
+    args = []
+    for a in arrays_and_scalars:
+        if isinstance(a, np.ndarray):
+            args.append(_fp(a))
+        elif isinstance(a, (int, np.integer)):
+            args.append(ctypes.c_int(int(a)))
+        else:
+            args.append(ctypes.c_float(float(a)))
+    ah, astride = shape
+    getattr(lib(), 'ref_' + name)(*args, ctypes.c_int(astride), ctypes.c_int(ah))
+
+
+def ref_set_gauss(coefs):
+    import numpy as np
+    lib().ref_set_gauss(_fp(np.ascontiguousarray(coefs, np.float32)))
+
+
+def ref_convert(fmt, src, w, h, seeds, gutter=12):
+    """Reference pixel-format kernel `f32_to_<fmt>`; seeds: uint32 [262144][3]."""
+    import ctypes
+    import numpy as np
+    src = np.ascontiguousarray(src, np.float32)
+    seeds = np.array(seeds, np.uint32)
+    assert seeds.shape[0] >= 262144
+    nbytes = {'rgba_u8': 4, 'rgba_u16': 8, 'yuv444p': 3, 'yuv444p10': 6, 'yuv420p10': 3,
+              'yuv444p12': 6}[fmt] * w * h
+    # slack: the reference's `>` bounds tests let the x = w/2, y = h/2 threads of the
+    # 4:2:0 kernel write past the chroma planes (code/output.py:164,186-189)
+    out = np.zeros(nbytes + 8 * w + 64, np.uint8)
+    getattr(lib(), 'ref_f32_to_' + fmt)(_fp(out), _fp(src), ctypes.c_int(gutter), ctypes.c_int(w),
+                                        ctypes.c_int(src.shape[1]), ctypes.c_int(h), _fp(seeds))
+    return out[:nbytes].view(np.uint8 if fmt in ('rgba_u8', 'yuv444p') else np.uint16)
+
+
+def ref_palette(ptimes, pals, seeds, tstart, tstep, rows=64):
+    """Reference interp_palette_flat: returns (uint32 [rows][256][2] packed, seeds)."""
+    import ctypes
+    import numpy as np
+    ptimes = np.ascontiguousarray(ptimes, np.float32)
+    pals = np.ascontiguousarray(pals, np.float32)
+    seeds = np.array(seeds, np.uint32)
+    out = np.zeros((rows, 256, 2), np.uint32)
+    lib().ref_interp_palette(_fp(out), _fp(seeds), _fp(ptimes), _fp(pals), ctypes.c_float(tstart),
+                             ctypes.c_float(tstep), ctypes.c_int(rows))
+    return out, seeds
 
 
 if __name__ == '__main__':

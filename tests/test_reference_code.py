@@ -172,3 +172,264 @@ def test_device_variation_vs_reference_code(native, built, name):
     err = np.maximum(np.abs(gx - ox), np.abs(gy - oy)) / (1.0 + np.maximum(np.abs(ox), np.abs(oy)))
     badfrac = np.mean(err[ok] > 2e-4)
     assert badfrac <= (0.02 if name in _DISCONTINUOUS else 0.0), (name, badfrac, float(err[ok].max()))
+
+
+# ---- precalc hunks (code/iter.py:56-95, variation precalcs) ----------------------------
+def test_precalc_equals_reference_code(built):
+    B = _ref()
+    from oracle import flame_ref as R
+    from cuburn_b200 import samples
+    rs = np.random.RandomState(4)
+    for trial in range(25):
+        g = samples.g3()
+        cam = dict(rotation=float(rs.uniform(-400, 400)), scale=float(rs.uniform(0.05, 3)),
+                   center=dict(x=float(rs.uniform(-2, 2)), y=float(rs.uniform(-2, 2))))
+        aff = dict(angle=float(rs.uniform(-720, 720)), spread=float(rs.uniform(-180, 180)),
+                   magnitude=dict(x=float(rs.uniform(0.05, 2)), y=float(rs.uniform(0.05, 2))),
+                   offset=dict(x=float(rs.uniform(-1, 1)), y=float(rs.uniform(-1, 1))))
+        g['camera'] = cam
+        g['xforms']['0']['pre_affine'] = aff
+        g['xforms']['0']['variations'] = {
+            'waves': {'weight': 0.1}, 'linear': {'weight': 0.5},
+            'perspective': {'weight': 0.1, 'angle': float(rs.uniform(-2, 2)), 'dist': float(rs.uniform(0.1, 4))},
+            'julian': {'weight': 0.1, 'power': float(rs.uniform(0.5, 6)), 'dist': float(rs.uniform(0.1, 3))},
+            'curve': {'weight': 0.1, 'xlength': float(rs.uniform(0.1, 3)), 'ylength': float(rs.uniform(0.1, 3))}}
+        w, h = 1920, 1080
+        ev = R.GenomeEval(g, w, h, 0.5, 0.0)
+        v = {k: float(a[0]) for k, a in ev.values.items()}
+        d = ev.dim
+
+        def close(got, want, what):
+            assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (what, got, want)
+        out = B.ref_precalc('camera', {'in_cam_rotation': cam['rotation'], 'in_cam_scale': cam['scale'],
+                                       'in_cam_center_x': cam['center']['x'],
+                                       'in_cam_center_y': cam['center']['y']}, w, d['aw'], d['ah'])
+        for c in ('xx', 'xy', 'xo', 'yx', 'yy', 'yo'):
+            close(v['camera.' + c], out['out_cam_' + c], 'camera.' + c)
+        out = B.ref_precalc('affine', {'in_px_angle': aff['angle'], 'in_px_spread': aff['spread'],
+                                       'in_px_magnitude_x': aff['magnitude']['x'],
+                                       'in_px_magnitude_y': aff['magnitude']['y'],
+                                       'in_px_offset_x': aff['offset']['x'],
+                                       'in_px_offset_y': aff['offset']['y']})
+        for c in ('xx', 'xy', 'xo', 'yx', 'yy', 'yo'):
+            close(v['xforms.0.pre_affine.' + c], out['out_px_' + c], 'affine.' + c)
+        vs = g['xforms']['0']['variations']
+        out = B.ref_precalc('waves', {'in_px_pre_affine_offset_x': aff['offset']['x'],
+                                      'in_px_pre_affine_offset_y': aff['offset']['y']})
+        close(v['xforms.0.variations.waves.dx2'], out['out_pv_dx2'], 'dx2')
+        close(v['xforms.0.variations.waves.dy2'], out['out_pv_dy2'], 'dy2')
+        out = B.ref_precalc('perspective', {'in_pv_angle': vs['perspective']['angle'],
+                                            'in_pv_dist': vs['perspective']['dist']})
+        for n in ('mdist', 'sin', 'cos'):
+            close(v['xforms.0.variations.perspective.' + n], out['out_pv_' + n], n)
+        out = B.ref_precalc('julian', {'in_pv_dist': vs['julian']['dist'], 'in_pv_power': vs['julian']['power']})
+        close(v['xforms.0.variations.julian.cn'], out['out_pv_cn'], 'cn')
+        out = B.ref_precalc('curve', {'in_pv_xlength': vs['curve']['xlength'],
+                                      'in_pv_ylength': vs['curve']['ylength']})
+        close(v['xforms.0.variations.curve.x2'], out['out_pv_x2'], 'x2')
+        close(v['xforms.0.variations.curve.y2'], out['out_pv_y2'], 'y2')
+
+
+# ---- palette (code/interp.py:372-433) -------------------------------------------------------
+@pytest.mark.parametrize('npal', [1, 3])
+def test_palette_equals_reference_code(built, npal):
+    """Same stream assignment (block r -> slot r), same arithmetic => identical levels."""
+    B = _ref()
+    from cuburn_b200 import samples, mwc
+    from oracle import flame_ref as R
+    g = samples.g6f()
+    if npal == 3:
+        g['palette'] = [[0.0] + samples.make_palette('spectrum'), [0.5] + samples.make_palette('fire'),
+                        [1.0] + samples.make_palette('ocean')]
+    ts, td = 0.35, 0.2
+    seeds = mwc.make_seeds(262144, host_seed=3)
+    mine, mseeds = R.palette_table(g, ts, td, seeds)
+    pals = sorted((float(p[0]), R.decode_palette(p[1:])) for p in g['palette'])
+    ptimes = np.full(32, 1e9, np.float32)
+    ptimes[:len(pals)] = [p[0] for p in pals]
+    src = np.zeros((32, 256, 4), np.float32)
+    for i, p in enumerate(pals):
+        src[i] = p[1]
+    packed, rseeds = B.ref_palette(ptimes, src, seeds, np.float32(ts), np.float32(td / 64))
+    lo, hi = packed[..., 0].astype(np.uint64), packed[..., 1].astype(np.uint64)
+    # out.y = (1 << 22) | (y << 4);  out.x = (u << 18) | v   (interp.py:428-429)
+    y = (hi >> np.uint64(4)) & np.uint64(0xff)
+    u = (lo >> np.uint64(18)) & np.uint64(0xff)
+    v = lo & np.uint64(0xff)
+    assert np.all((hi >> np.uint64(22)) == 1)
+    lv = np.round(mine[..., :3] * 255).astype(np.uint64)
+    assert np.array_equal(lv[..., 0], y) and np.array_equal(lv[..., 1], u) and np.array_equal(lv[..., 2], v)
+    assert np.array_equal(mseeds[:16384], rseeds[:16384])
+
+
+# ---- filters (code/filters.py) ----------------------------------------------------------------
+def _field(seed, w=200, h=88, kind='mixed'):
+    from oracle import flame_ref as R
+    d = R.calc_dim(w, h)
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:d['ah'], 0:d['astride']]
+    den = 40 * np.exp(-((xx - 90) ** 2 + (yy - 50) ** 2) / 600.0)
+    den += 5 * (np.sin(xx / 7.0) > 0.3) * (yy > 20) * (yy < 70)
+    den += np.where((xx < 6) | (yy < 5) | (xx > d['astride'] - 7), 12.0, 0.0)
+    den[30:60, 130:170] = 0
+    den *= rs.uniform(0.7, 1.3, den.shape)
+    f = np.zeros((d['ah'], d['astride'], 4), np.float32)
+    f[..., 3] = den
+    for ch, ph in enumerate((0.0, 2.0, 4.0)):
+        f[..., ch] = den * (0.5 + 0.45 * np.sin(xx / 23.0 + yy / 31.0 + ph))
+    if kind == 'points':
+        f[...] = 0
+    for (py, px, val) in ((10, 10, 300.0), (60, 150, 5000.0), (100, 200, 50.0), (55, 3, 800.0)):
+        f[py, px] += np.array([0.8 * val, 0.3 * val, 0.1 * val, val], np.float32)
+    return d, f
+
+
+def _close(got, want, rel, what):
+    scale = max(float(np.abs(want).max()), 1e-6)
+    bad = np.abs(got - want) > rel * scale + rel * np.abs(want)
+    assert not np.isnan(got).any(), what
+    assert bad.mean() == 0, (what, float(np.abs(got - want).max()), scale)
+
+
+def test_pointwise_filters_equal_reference_code(built):
+    B = _ref()
+    from oracle import filters_ref as F
+    d, f = _field(1)
+    shape = f.shape[:2]
+    out = np.zeros_like(f)
+    g = f.copy()
+    g[..., 1] += 0.5 * g[..., 3]
+    g[..., 2] += 0.5 * g[..., 3]
+    B.ref_filter('yuv_to_rgb', out, g, shape=shape)
+    _close(F.yuv_to_rgb(g), out, 1e-6, 'yuv_to_rgb')
+    k1, k2 = F.logscale_consts(4, 0.28, 200, 88, 256)
+    B.ref_filter('logscale', out, f, k1, k2, shape=shape)
+    lf = F.logscale(f, k1, k2)
+    _close(lf, np.nan_to_num(out), 1e-5, 'logscale')
+    gam, lin, lingam = F.calc_lingam(4, 0.01)
+    pix = lf.copy()
+    B.ref_filter('plainclip', pix, gam - 1, lin, lingam, 1.3, shape=shape)
+    _close(F.plainclip(lf, 1.3), pix, 1e-5, 'plainclip')
+    for vib, hp in ((1.0, -1.0), (0.6, 2.0), (0.8, -0.4)):
+        pix = lf.copy()
+        B.ref_filter('colorclip', pix, vib, hp, gam, lin, lingam, shape=shape)
+        _close(F.colorclip(lf, vib, hp), pix, 1e-5, 'colorclip')
+    B.ref_filter('logencode', out, lf + np.float32(1e-3), 2.2, shape=shape)
+    _close(F.logencode(lf + np.float32(1e-3)), out, 1e-5, 'logencode')
+
+
+@pytest.mark.parametrize('pattern', list(range(16)))
+def test_blurs_equal_reference_code(built, pattern):
+    B = _ref()
+    from oracle import filters_ref as F
+    d, f = _field(2)
+    shape = f.shape[:2]
+    for up, stdev in ((0, 1), (1, 0.7)):
+        coefs = F.gauss_coefs(stdev)
+        B.ref_set_gauss(coefs)
+        o1 = np.zeros(shape, np.float32)
+        B.ref_filter('den_blur', o1, f, pattern, up, shape=shape)
+        _close(F.blur7(f[..., 3], pattern, up, coefs), o1, 1e-6, 'den_blur')
+        plane = np.ascontiguousarray(f[..., 0])
+        B.ref_filter('den_blur_1c', o1, plane, pattern, up, shape=shape)
+        _close(F.blur7(plane, pattern, up, coefs), o1, 1e-6, 'den_blur_1c')
+        o4 = np.zeros_like(f)
+        B.ref_filter('full_blur', o4, f, pattern, up, shape=shape)
+        _close(F.blur7(f, pattern, up, coefs), o4, 1e-6, 'full_blur')
+
+
+@pytest.mark.parametrize('pattern', [0, 1, 2, 5, 7])
+@pytest.mark.parametrize('kind', ['mixed', 'points'])
+def test_bilateral_equals_reference_code(built, pattern, kind):
+    B = _ref()
+    from oracle import filters_ref as F
+    d, f = _field(3, kind=kind)
+    shape = f.shape[:2]
+    args = dict(sstd=6 * 200 / 1920. * 4, cstd=0.05, dstd=1.5, dpow=0.8, gspeed=4.0)
+    coefs = F.gauss_coefs(1)
+    B.ref_set_gauss(coefs)
+    b0, b1 = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+    B.ref_filter('den_blur', b0, f, pattern, 0, shape=shape)
+    B.ref_filter('den_blur_1c', b1, b0, pattern, 1, shape=shape)
+    out = np.zeros_like(f)
+    B.ref_filter('bilateral', out, f, b1, pattern, 15, args['sstd'], args['cstd'], args['dstd'],
+                 args['dpow'], args['gspeed'], shape=shape)
+    want = F.bilateral_pass(f, pattern, 15, args['sstd'], args['cstd'], args['dstd'], args['dpow'],
+                            args['gspeed'])
+    scale = float(np.abs(out).max())
+    err = np.abs(want - out)
+    assert (err > 1e-4 * scale + 1e-4 * np.abs(out)).mean() < 1e-4, float(err.max())
+
+
+def test_clip_recipes_equal_reference_code(built):
+    """smearclip and haloclip as the host recipes chain them (cuburn/filters.py:110-163)."""
+    B = _ref()
+    from oracle import filters_ref as F
+    d, f = _field(5)
+    shape = f.shape[:2]
+    k1, k2 = F.logscale_consts(4, 0.28, 200, 88, 256)
+    lf = F.logscale(f, k1, k2)
+    gam, lin, lingam = F.calc_lingam(4, 0.01)
+    # smearclip
+    B.ref_set_gauss(F.gauss_coefs(0.7))
+    a, b = np.zeros_like(lf), np.zeros_like(lf)
+    B.ref_filter('apply_gamma_full_hi', a, lf.copy(), gam - 1, shape=shape)
+    for pattern, (src, dst) in zip((2, 3, 0, 1), ((a, b), (b, a), (a, b), (b, a))):
+        B.ref_filter('full_blur', dst, src, pattern, 0, shape=shape)
+    pix = lf.copy()
+    B.ref_filter('smearclip', pix, a, gam - 1, lin, lingam, shape=shape)
+    _close(F.smearclip(lf), pix, 2e-5, 'smearclip')
+    # haloclip
+    B.ref_set_gauss(F.gauss_coefs(1))
+    p0, p1 = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+    B.ref_filter('apply_gamma', p0, lf.copy(), 0.1, shape=shape)
+    B.ref_filter('den_blur_1c', p1, p0, 2, 0, shape=shape)
+    B.ref_filter('den_blur_1c', p0, p1, 3, 0, shape=shape)
+    pix = lf.copy()
+    B.ref_filter('haloclip', pix, p0, np.float32(1 / 4.0 - 1), shape=shape)
+    _close(F.haloclip(lf), pix, 2e-5, 'haloclip')
+
+
+# ---- pixel formats (code/output.py) ---------------------------------------------------------------
+@pytest.mark.parametrize('fmt', ['rgba_u8', 'rgba_u16', 'yuv444p', 'yuv444p10', 'yuv420p10', 'yuv444p12'])
+def test_output_equals_reference_code(built, fmt):
+    """The reference hands RNG streams to blocks through a ring buffer; ours are
+    owned by pixel lanes.  Same maths, different dither draws: levels agree to +-1,
+    and exactly wherever no dither is involved."""
+    B = _ref()
+    from cuburn_b200 import mwc
+    from oracle import flame_ref as R, output_ref as O
+    w, h = 128, 72                       # multiples of the 32 x 8 launch tile
+    d = R.calc_dim(w, h)
+    rs = np.random.RandomState(6)
+    src = rs.uniform(-0.2, 1.3, (d['ah'], d['astride'], 4)).astype(np.float32)
+    src[rs.rand(d['ah'], d['astride']) < 0.2] = 0
+    src[..., 3] = np.abs(src[..., 3])
+    seeds = mwc.make_seeds(262144, host_seed=9)
+    ref = B.ref_convert(fmt, src, w, h, seeds).astype(np.int64)
+    mine = O.convert(fmt, src, w, h, seeds)[0].reshape(-1).astype(np.int64)
+    assert ref.shape == mine.shape
+    diff = np.abs(ref - mine)
+    crop = src[12:12 + h, 12:12 + w]
+    if fmt == 'yuv444p10':
+        # the reference stores U without dither or clamp (a negative float -> u16
+        # conversion); we clamp.  Compare U only where it is in range.
+        cb = (-0.168736 * crop[..., 0] - 0.331264 * crop[..., 1] + 0.5 * crop[..., 2] + 0.5).reshape(-1)
+        diff[w * h:2 * w * h][(cb < 0) | (cb > 1)] = 0
+    if fmt == 'yuv420p10':
+        # the reference's bounds tests are `>`: its x = w/2 threads overwrite chroma
+        # column 0 of the next row and its y = h/2 threads write Cb values over row 0
+        # of the Cr plane (code/output.py:164,186-189); ignore those cells
+        for plane in (0, 1):
+            base = w * h + plane * (w * h // 4)
+            view = diff[base: base + w * h // 4].reshape(h // 2, w // 2)
+            view[:, 0] = 0
+            if plane == 1:
+                view[0, :] = 0
+    assert diff.max() <= 1, int(diff.max())
+    if fmt in ('rgba_u8', 'rgba_u16'):
+        zero = (crop <= 0).reshape(-1)
+        assert np.all(ref[zero] == 0) and np.all(mine[zero] == 0)
+        peak = 255 if fmt == 'rgba_u8' else 65535
+        sat = (crop >= 1.0).reshape(-1)
+        assert np.all(ref[sat] == peak) and np.all(mine[sat] == peak)
