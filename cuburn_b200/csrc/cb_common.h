@@ -13,6 +13,7 @@ void cb_set_error(const char *fmt, ...);
     do {                                                                      \
         cudaError_t err__ = (expr);                                           \
         if (err__ != cudaSuccess) {                                           \
+            (void)cudaGetLastError(); /* do not leave it for a later check */ \
             cb_set_error("%s failed: %s (%s:%d)", #expr,                      \
                          cudaGetErrorString(err__), __FILE__, __LINE__);      \
             return err__ == cudaErrorMemoryAllocation ? CB_ERR_NOMEM          \

@@ -433,3 +433,94 @@ def test_output_equals_reference_code(built, fmt):
         peak = 255 if fmt == 'rgba_u8' else 65535
         sat = (crop >= 1.0).reshape(-1)
         assert np.all(ref[sat] == peak) and np.all(mine[sat] == peak)
+
+
+# ---- device vs the reference's code, directly (GPU box) ----------------------------------------
+@pytest.mark.gpu
+def test_device_palette_vs_reference_code(native, built):
+    B = _ref()
+    N = native
+    from cuburn_b200 import samples, mwc
+    from oracle import flame_ref as R
+    g = samples.g6f()
+    g['palette'] = [[0.0] + samples.make_palette('spectrum'), [0.4] + samples.make_palette('fire'),
+                    [1.0] + samples.make_palette('ocean')]
+    ts, td = 0.2, 0.5
+    seeds = mwc.make_seeds(262144, host_seed=4)
+    pals = sorted((float(p[0]), R.decode_palette(p[1:])) for p in g['palette'])
+    ptimes = np.full(32, 1e9, np.float32)
+    ptimes[:3] = [p[0] for p in pals]
+    src = np.zeros((32, 256, 4), np.float32)
+    for i, p in enumerate(pals):
+        src[i] = p[1]
+    d_pal, d_seeds = N.DeviceBuffer(64 * 256 * 16), N.to_device(seeds)
+    d_pt, d_src = N.to_device(ptimes), N.to_device(src)
+    N.check(N.lib().cb_interp_palette(d_pal.ptr, d_seeds.ptr, d_pt.ptr, d_src.ptr,
+                                      np.float32(ts), np.float32(td / 64), 64, None))
+    N.check(N.lib().cb_device_sync())
+    dev = N.from_device(d_pal, (64, 256, 4), np.float32)
+    packed, rseeds = B.ref_palette(ptimes, src, seeds, np.float32(ts), np.float32(td / 64))
+    lo, hi = packed[..., 0].astype(np.uint64), packed[..., 1].astype(np.uint64)
+    lv = np.round(dev[..., :3] * 255).astype(np.uint64)
+    assert np.array_equal(lv[..., 0], (hi >> np.uint64(4)) & np.uint64(0xff))
+    assert np.array_equal(lv[..., 1], (lo >> np.uint64(18)) & np.uint64(0xff))
+    assert np.array_equal(lv[..., 2], lo & np.uint64(0xff))
+    assert np.array_equal(N.from_device(d_seeds, seeds.shape, np.uint32), rseeds)
+
+
+@pytest.mark.gpu
+def test_device_filters_vs_reference_code(native, built):
+    """Device kernels (fast-math SFU intrinsics) vs the reference's kernels on the CPU."""
+    B = _ref()
+    N = native
+    from oracle import filters_ref as F
+    from cuburn_b200.filters import gauss_coefs
+    L = N.lib()
+    d, f = _field(8)
+    dim = N.calc_dim(200, 88)
+    shape = f.shape[:2]
+    up = lambda a: N.to_device(np.ascontiguousarray(a, np.float32))
+    # logscale + colorclip + plainclip
+    k1, k2 = F.logscale_consts(4, 0.28, 200, 88, 256)
+    ref = np.zeros_like(f)
+    B.ref_filter('logscale', ref, f, k1, k2, shape=shape)
+    ref = np.nan_to_num(ref)
+    buf = up(f)
+    N.check(L.cb_logscale(buf.ptr, buf.ptr, k1, k2, N.byref(dim), None))
+    _close(N.from_device(buf, f.shape, np.float32), ref, 1e-4, 'logscale')
+    gam, lin, lingam = F.calc_lingam(4, 0.01)
+    for vib, hp in ((1.0, -1.0), (0.7, 1.5)):
+        want = ref.copy()
+        B.ref_filter('colorclip', want, vib, hp, gam, lin, lingam, shape=shape)
+        buf = up(ref)
+        N.check(L.cb_colorclip(buf.ptr, np.float32(vib), np.float32(hp), gam, lin, lingam,
+                               N.byref(dim), None))
+        _close(N.from_device(buf, f.shape, np.float32), want, 2e-4, 'colorclip')
+    # blurs, all three kernels, a few directions
+    for pattern in (0, 3, 6, 9, 14):
+        c = F.gauss_coefs(1)
+        B.ref_set_gauss(c)
+        want = np.zeros_like(f)
+        B.ref_filter('full_blur', want, f, pattern, 0, shape=shape)
+        src, dst = up(f), N.DeviceBuffer(f.nbytes)
+        N.check(L.cb_full_blur(dst.ptr, src.ptr, pattern, 0, gauss_coefs(1), N.byref(dim), None))
+        _close(N.from_device(dst, f.shape, np.float32), want, 1e-5, 'full_blur')
+    # one bilateral direction: the fused device pass vs the reference's three kernels
+    for pattern in (1, 4):
+        args = dict(sstd=6 * 200 / 1920. * 4, cstd=0.05, dstd=1.5, dpow=0.8, gspeed=4.0)
+        B.ref_set_gauss(F.gauss_coefs(1))
+        b0, b1 = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+        B.ref_filter('den_blur', b0, f, pattern, 0, shape=shape)
+        B.ref_filter('den_blur_1c', b1, b0, pattern, 1, shape=shape)
+        want = np.zeros_like(f)
+        B.ref_filter('bilateral', want, f, b1, pattern, 15, args['sstd'], args['cstd'],
+                     args['dstd'], args['dpow'], args['gspeed'], shape=shape)
+        src, scratch, dst = up(f), N.DeviceBuffer(f.nbytes), N.DeviceBuffer(f.nbytes)
+        N.check(L.cb_bilateral_direction(
+            dst.ptr, src.ptr, scratch.ptr, pattern, 15, gauss_coefs(1), np.float32(args['sstd']),
+            np.float32(args['cstd']), np.float32(args['dstd']), np.float32(args['dpow']),
+            np.float32(args['gspeed']), N.byref(dim), None))
+        N.check(L.cb_device_sync())
+        got = N.from_device(dst, f.shape, np.float32)
+        scale = float(np.abs(want).max())
+        assert (np.abs(got - want) > 2e-3 * scale + 2e-3 * np.abs(want)).mean() < 1e-3

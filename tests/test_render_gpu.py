@@ -120,3 +120,56 @@ def test_errors_are_loud(native, built):
         N.check(N.lib().cb_den_blur(0, 0, 99, 0, None, N.byref(N.calc_dim(64, 64)), None))
     with pytest.raises(MemoryError):
         N.DeviceBuffer(1 << 46)
+
+
+def test_resize_and_reuse_manager(native, built):
+    """One manager renders different sizes back to back (Framebuffers.alloc grows,
+    never shrinks; dims are always recomputed) and different genomes."""
+    N = native
+    from cuburn_b200 import samples, render
+    rmgr = render.RenderManager(seed=6)
+    sizes = [(320, 180), (640, 360), (200, 88), (640, 360)]
+    frames = []
+    for (w, h), gname in zip(sizes, ('G3', 'G6F', 'G3', 'G6F')):
+        gnm = samples.GENOMES[gname]()
+        gprof, tc = still_profile(gnm, w, h, 40)
+        rdr = render.Renderer(gnm, gprof)
+        evt, frame = rmgr.queue_frame(rdr, gnm, gprof, tc)
+        evt.synchronize()
+        frames.append(np.array(frame))
+        assert frame.shape == (h, w, 4) and frame[..., :3].max() > 0
+        dim = rmgr.fb.calc_dim(w, h)
+        assert rmgr.fb.nbins >= dim.ah * dim.astride
+    assert rmgr.fb.nbins == 384 * 672            # grew to the largest request, kept it
+    # nothing of a larger earlier frame bleeds into a smaller later one
+    assert frames[2][:, -1, 3].max() <= 255 and np.isfinite(frames[2]).all()
+    rmgr.fb.free()
+    assert rmgr.fb.d_front is None and rmgr.fb.nbins is None
+
+
+def test_other_filter_chains_and_outputs(native, built):
+    """colorclip / haloclip / plainclip / logencode chains and 16-bit + planar outputs
+    run through queue_frame and give sane frames."""
+    from cuburn_b200 import samples, render, profile
+    gnm = samples.g6f()
+    rmgr = render.RenderManager(seed=12)
+    base = dict(width=320, height=180, spp=100, frame_width=0, start=1, end=2)
+    cases = [
+        (['bilateral', 'logscale', 'colorclip'], dict(type='png'), (180, 320, 4), np.uint8),
+        (['logscale', 'haloclip'], dict(type='tiff'), (180, 320, 4), np.uint16),
+        (['logscale', 'plainclip'], dict(type='raw', pix_fmt='yuv444p10'), (3, 180, 320), np.uint16),
+        (['logscale', 'smearclip'], dict(type='raw', pix_fmt='yuv420p10'), (180 * 320 * 3 // 2,), np.uint16),
+        (['logscale', 'colorclip', 'logencode'], dict(type='raw', pix_fmt='yuv444p12'), (3, 180, 320), np.uint16),
+    ]
+    for order, out, shape, dt in cases:
+        prof = dict(base, filter_order=order, output=out)
+        gprof = profile.wrap(prof, gnm)
+        tc = profile.enumerate_times(gprof)[0][1][0]
+        rdr = render.Renderer(gnm, gprof)
+        assert [f.name for f in rdr.filts] == ['yuv'] + order
+        evt, frame = rmgr.queue_frame(rdr, gnm, gprof, tc)
+        evt.synchronize()
+        assert frame.shape == shape and frame.dtype == dt
+        assert frame.max() > frame.min()
+        media, logs = rdr.out.encode(frame)
+        assert len(media) == 1 and len(next(iter(media.values())).read()) > 1000
