@@ -18,12 +18,65 @@
 #define CB_2PI     6.28318548202515f
 #define CB_LOG2E   1.44269502162933f
 
+// ---- compact elementary functions ------------------------------------------------------
+// --use_fast_math turns sin/cos/exp/log/pow/div/sqrt into 1-2 SFU instructions, but
+// atan2f (~42 instructions), sinhf/coshf (~23 each) and fmodf (~60) stay library
+// routines and dominate the heavier variations.  These replacements keep the error
+// at the level of the SFU intrinsics used everywhere else (atan2: 3.2e-7 rad max;
+// sinh/cosh: a few ulp; fmod: exact quotient truncation in float) at a third of the
+// issue slots.  Define CB_FAST_LIBM 0 to fall back to the CUDA math library.
+#ifndef CB_FAST_LIBM
+#define CB_FAST_LIBM 1
+#endif
+
+#if CB_FAST_LIBM
+__device__ __forceinline__ float v_atan2(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = __fdividef(mn, fmaxf(mx, 1.0e-37f));          // in [0, 1]
+    float s = a * a;
+    // minimax fit of atan(a)/a in s = a^2 on [0, 1]
+    float p = 0.006811772007495165f;
+    p = fmaf(p, s, -0.033604152500629425f);
+    p = fmaf(p, s, 0.07962358742952347f);
+    p = fmaf(p, s, -0.13233336806297302f);
+    p = fmaf(p, s, 0.19807814061641693f);
+    p = fmaf(p, s, -0.3331736922264099f);
+    p = fmaf(p, s, 0.9999961256980896f);
+    float r = p * a;
+    if (ay > ax) r = 1.57079637050629f - r;
+    if (x < 0.0f) r = 3.14159274101257f - r;
+    return copysignf(r, y);
+}
+
+__device__ __forceinline__ void v_sinhcosh(float x, float &sh, float &ch) {
+    float e = __expf(x);
+    float ie = __fdividef(1.0f, e);
+    ch = 0.5f * (e + ie);
+    sh = 0.5f * (e - ie);
+    if (fabsf(x) < 0.25f) {                                  // avoid cancellation near 0
+        float x2 = x * x;
+        sh = x * fmaf(x2, fmaf(x2, fmaf(x2, 1.0f / 5040.0f, 1.0f / 120.0f), 1.0f / 6.0f), 1.0f);
+    }
+}
+
+__device__ __forceinline__ float v_fmod(float x, float y) {
+    return x - y * truncf(__fdividef(x, y));
+}
+#else
+__device__ __forceinline__ float v_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ void v_sinhcosh(float x, float &sh, float &ch) { sh = sinhf(x); ch = coshf(x); }
+__device__ __forceinline__ float v_fmod(float x, float y) { return fmodf(x, y); }
+#endif
+__device__ __forceinline__ float v_sinh(float x) { float s, c; v_sinhcosh(x, s, c); return s; }
+__device__ __forceinline__ float v_cosh(float x) { float s, c; v_sinhcosh(x, s, c); return c; }
+
 __device__ __forceinline__ float v_r2(float x, float y) { return x * x + y * y; }
 __device__ __forceinline__ float v_r(float x, float y) { return sqrtf(x * x + y * y); }
 // flam3's "atan2(x, y)" convention (angle measured from the +y axis)
-__device__ __forceinline__ float v_atan_xy(float x, float y) { return atan2f(x, y); }
+__device__ __forceinline__ float v_atan_xy(float x, float y) { return v_atan2(x, y); }
 // the mathematical convention
-__device__ __forceinline__ float v_atan_yx(float x, float y) { return atan2f(y, x); }
+__device__ __forceinline__ float v_atan_yx(float x, float y) { return v_atan2(y, x); }
 
 // ---- 0..12 -----------------------------------------------------------------
 VFN var_linear(float tx, float ty, float w, float &ox, float &oy) {
@@ -164,14 +217,14 @@ VFN var_power(float tx, float ty, float w, float &ox, float &oy) {
 
 VFN var_cosine(float tx, float ty, float w, float &ox, float &oy) {
     float a = CB_PI * tx;
-    ox += w * cosf(a) * coshf(ty);
-    oy -= w * sinf(a) * sinhf(ty);
+    ox += w * cosf(a) * v_cosh(ty);
+    oy -= w * sinf(a) * v_sinh(ty);
 }
 
 VFN var_rings(float tx, float ty, float w, float &ox, float &oy, float xo) {
     float d = xo * xo;
     float r = v_r(tx, ty), a = v_atan_xy(tx, ty);
-    r = w * (fmodf(r + d, 2.0f * d) - d + r * (1.0f - d));
+    r = w * (v_fmod(r + d, 2.0f * d) - d + r * (1.0f - d));
     ox += r * cosf(a);
     oy += r * sinf(a);
 }
@@ -181,7 +234,7 @@ VFN var_fan(float tx, float ty, float w, float &ox, float &oy,
     float d = xo * xo * CB_PI;
     float h = 0.5f * d;
     float a = v_atan_xy(tx, ty);
-    a += (fmodf(a + yo, d) > h) ? -h : h;
+    a += (v_fmod(a + yo, d) > h) ? -h : h;
     float r = w * v_r(tx, ty);
     ox += r * cosf(a);
     oy += r * sinf(a);
@@ -469,11 +522,11 @@ VFN var_bipolar(float tx, float ty, float w, float &ox, float &oy,
     float t = rr + 1.0f;
     float x2 = tx * 2.0f;
     float ps = -CB_PI_2 * shift;
-    float y = 0.5f * atan2f(2.0f * ty, rr - 1.0f) + ps;
+    float y = 0.5f * v_atan2(2.0f * ty, rr - 1.0f) + ps;
     if (y > CB_PI_2)
-        y = -CB_PI_2 + fmodf(y + CB_PI_2, CB_PI);
+        y = -CB_PI_2 + v_fmod(y + CB_PI_2, CB_PI);
     else if (y < -CB_PI_2)
-        y = CB_PI_2 - fmodf(CB_PI_2 - y, CB_PI);
+        y = CB_PI_2 - v_fmod(CB_PI_2 - y, CB_PI);
     ox += w * 0.25f * CB_2_PI * logf((t + x2) / (t - x2));
     oy += w * CB_2_PI * y;
 }
@@ -546,8 +599,8 @@ VFN var_edisc(float tx, float ty, float w, float &ox, float &oy) {
     float nw = w / 11.57034632f;
     float sn = sinf(a1), cs = cosf(a1);
     if (ty > 0.0f) sn = -sn;
-    ox += nw * coshf(a2) * cs;
-    oy += nw * sinhf(a2) * sn;
+    ox += nw * v_cosh(a2) * cs;
+    oy += nw * v_sinh(a2) * sn;
 }
 
 VFN var_elliptic(float tx, float ty, float w, float &ox, float &oy) {
@@ -560,7 +613,7 @@ VFN var_elliptic(float tx, float ty, float w, float &ox, float &oy) {
     float nw = w / CB_PI_2;
     b = (b < 0.0f) ? 0.0f : sqrtf(b);
     ssx = (ssx < 0.0f) ? 0.0f : sqrtf(ssx);
-    ox += nw * atan2f(a, b);
+    ox += nw * v_atan2(a, b);
     float l = nw * logf(xmax + ssx);
     if (ty > 0.0f) oy += l; else oy -= l;
 }
@@ -589,7 +642,7 @@ VFN var_lazysusan(float tx, float ty, float w, float &ox, float &oy,
     float x = tx - lx, y = ty + ly;
     float r = v_r(x, y);
     if (r < w) {
-        float a = atan2f(y, x) + spin + twist * (w - r);
+        float a = v_atan2(y, x) + spin + twist * (w - r);
         ox += w * (r * cosf(a) + lx);
         oy += w * (r * sinf(a) - ly);
     } else {
@@ -618,8 +671,8 @@ VFN var_pre_blur(float &tx, float &ty, float w, float &ox, float &oy,
 
 __device__ __forceinline__ float v_modulus1(float t, float m) {
     float span = 2.0f * m;
-    if (t > m) return -m + fmodf(t + m, span);
-    if (t < -m) return m - fmodf(m - t, span);
+    if (t > m) return -m + v_fmod(t + m, span);
+    if (t < -m) return m - v_fmod(m - t, span);
     return t;
 }
 
@@ -729,70 +782,70 @@ VFN var_log(float tx, float ty, float w, float &ox, float &oy) {
 }
 
 VFN var_sin(float tx, float ty, float w, float &ox, float &oy) {
-    ox += w * sinf(tx) * coshf(ty);
-    oy += w * cosf(tx) * sinhf(ty);
+    ox += w * sinf(tx) * v_cosh(ty);
+    oy += w * cosf(tx) * v_sinh(ty);
 }
 
 VFN var_cos(float tx, float ty, float w, float &ox, float &oy) {
-    ox += w * cosf(tx) * coshf(ty);
-    oy -= w * sinf(tx) * sinhf(ty);
+    ox += w * cosf(tx) * v_cosh(ty);
+    oy -= w * sinf(tx) * v_sinh(ty);
 }
 
 VFN var_tan(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 1.0f / (cosf(2.0f * tx) + coshf(2.0f * ty));
+    float k = 1.0f / (cosf(2.0f * tx) + v_cosh(2.0f * ty));
     ox += w * k * sinf(2.0f * tx);
-    oy += w * k * sinhf(2.0f * ty);
+    oy += w * k * v_sinh(2.0f * ty);
 }
 
 VFN var_sec(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 2.0f / (cosf(2.0f * tx) + coshf(2.0f * ty));
-    ox += w * k * cosf(tx) * coshf(ty);
-    oy += w * k * sinf(tx) * sinhf(ty);
+    float k = 2.0f / (cosf(2.0f * tx) + v_cosh(2.0f * ty));
+    ox += w * k * cosf(tx) * v_cosh(ty);
+    oy += w * k * sinf(tx) * v_sinh(ty);
 }
 
 VFN var_csc(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 2.0f / (coshf(2.0f * ty) - cosf(2.0f * tx));
-    ox += w * k * sinf(tx) * coshf(ty);
-    oy -= w * k * cosf(tx) * sinhf(ty);
+    float k = 2.0f / (v_cosh(2.0f * ty) - cosf(2.0f * tx));
+    ox += w * k * sinf(tx) * v_cosh(ty);
+    oy -= w * k * cosf(tx) * v_sinh(ty);
 }
 
 VFN var_cot(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 1.0f / (coshf(2.0f * ty) - cosf(2.0f * tx));
+    float k = 1.0f / (v_cosh(2.0f * ty) - cosf(2.0f * tx));
     ox += w * k * sinf(2.0f * tx);
-    oy += w * k * -1.0f * sinhf(2.0f * ty);
+    oy += w * k * -1.0f * v_sinh(2.0f * ty);
 }
 
 VFN var_sinh(float tx, float ty, float w, float &ox, float &oy) {
-    ox += w * sinhf(tx) * cosf(ty);
-    oy += w * coshf(tx) * sinf(ty);
+    ox += w * v_sinh(tx) * cosf(ty);
+    oy += w * v_cosh(tx) * sinf(ty);
 }
 
 VFN var_cosh(float tx, float ty, float w, float &ox, float &oy) {
-    ox += w * coshf(tx) * cosf(ty);
-    oy += w * sinhf(tx) * sinf(ty);
+    ox += w * v_cosh(tx) * cosf(ty);
+    oy += w * v_sinh(tx) * sinf(ty);
 }
 
 VFN var_tanh(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 1.0f / (cosf(2.0f * ty) + coshf(2.0f * tx));
-    ox += w * k * sinhf(2.0f * tx);
+    float k = 1.0f / (cosf(2.0f * ty) + v_cosh(2.0f * tx));
+    ox += w * k * v_sinh(2.0f * tx);
     oy += w * k * sinf(2.0f * ty);
 }
 
 VFN var_sech(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 2.0f / (cosf(2.0f * ty) + coshf(2.0f * tx));
-    ox += w * k * cosf(ty) * coshf(tx);
-    oy -= w * k * sinf(ty) * sinhf(tx);
+    float k = 2.0f / (cosf(2.0f * ty) + v_cosh(2.0f * tx));
+    ox += w * k * cosf(ty) * v_cosh(tx);
+    oy -= w * k * sinf(ty) * v_sinh(tx);
 }
 
 VFN var_csch(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 2.0f / (coshf(2.0f * tx) - cosf(2.0f * ty));
-    ox += w * k * sinhf(tx) * cosf(ty);
-    oy -= w * k * coshf(tx) * sinf(ty);
+    float k = 2.0f / (v_cosh(2.0f * tx) - cosf(2.0f * ty));
+    ox += w * k * v_sinh(tx) * cosf(ty);
+    oy -= w * k * v_cosh(tx) * sinf(ty);
 }
 
 VFN var_coth(float tx, float ty, float w, float &ox, float &oy) {
-    float k = 1.0f / (coshf(2.0f * tx) - cosf(2.0f * ty));
-    ox += w * k * sinhf(2.0f * tx);
+    float k = 1.0f / (v_cosh(2.0f * tx) - cosf(2.0f * ty));
+    ox += w * k * v_sinh(2.0f * tx);
     oy += w * k * sinf(2.0f * ty);
 }
 
@@ -800,7 +853,7 @@ VFN var_flux(float tx, float ty, float w, float &ox, float &oy, float spread) {
     float xp = tx + w, xm = tx - w;
     float r = w * (2.0f + spread)
             * sqrtf(sqrtf(ty * ty + xp * xp) / sqrtf(ty * ty + xm * xm));
-    float a = (atan2f(ty, xm) - atan2f(ty, xp)) * 0.5f;
+    float a = (v_atan2(ty, xm) - v_atan2(ty, xp)) * 0.5f;
     ox += r * cosf(a);
     oy += r * sinf(a);
 }

@@ -91,7 +91,8 @@ def test_nvrtc_compiles_every_variation(built):
 
 
 def test_sample_genome_modules_use_vector_red(built, tmp_path):
-    """SASS evidence: 16-byte float4 reductions and SFU intrinsics, no local memory."""
+    """SASS evidence: 16-byte float4 reductions and SFU intrinsics; the 32-register
+    cap (64 warps/SM, measured fastest) may cost a few bytes of spill, no more."""
     from cuburn_b200 import _native as N, samples
     from cuburn_b200.code import itergen
     hn, hs = itergen.load_headers()
@@ -105,7 +106,7 @@ def test_sample_genome_modules_use_vector_red(built, tmp_path):
     usage = subprocess.run(['cuobjdump', '-res-usage', str(p)], stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, text=True).stdout
     m = re.search(r'Function cb_iter:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)', usage)
-    assert m and int(m.group(2)) == 0 and int(m.group(4)) == 0 and int(m.group(1)) <= 64
+    assert m and int(m.group(2)) <= 64 and int(m.group(4)) == 0 and int(m.group(1)) <= 32
 
 
 def test_compile_error_carries_log(built):
