@@ -49,74 +49,134 @@ __device__ __forceinline__ int clamp_idx(int x, int y, int w, int h) {
     int yi = blockIdx.y * 8 + threadIdx.y;                        \
     int gi = yi * dim.astride + xi
 
-// ---- histogram layout ---------------------------------------------------------------
-// Inverse of the slice-balancing accumulation layout (device/iter_kernel.cuh).
-__global__ void __launch_bounds__(256)
-k_hist_unswizzle(float4 *dst, const float4 *src, int swizzle_bins) {
-    unsigned int i = blockIdx.x * 256 + threadIdx.x;
-    unsigned int j = (i & 0xffff0000u) | ((i * 40503u) & 0xffffu);
-    dst[i] = src[(int)i < swizzle_bins ? j : i];
-}
+// ---- pointwise kernels -------------------------------------------------------------
+// Each filter is a small functor; the three kernel templates below apply it to
+// PW_PER x 256 consecutive bins per CTA, with every thread issuing all of its
+// 16-byte loads before it uses any of them.  That keeps >= 64 KB in flight per SM,
+// which HBM3e needs to approach its copy bandwidth.  nbins is a multiple of 512
+// (astride % 32 == 0, aheight % 16 == 0); the last CTA is bounds-tested.
+#define PW_PER 4
 
-// ---- pointwise kernels: one float4 per thread, exact 1-D grid ---------------
+template <typename Op>
 __global__ void __launch_bounds__(256)
-k_yuv_to_rgb(float4 *dst, const float4 *src) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = src[i];
-    // remove the +0.5 per-sample chroma bias, then JPEG full-range YUV->RGB
-    float u = p.y - 0.5f * p.w, v = p.z - 0.5f * p.w;
-    float r = p.x + 1.402f * v;
-    float g = p.x - 0.34414f * u - 0.71414f * v;
-    float b = p.x + 1.772f * u;
-    dst[i] = make_float4(fmaxf(0.0f, r), fmaxf(0.0f, g), fmaxf(0.0f, b), p.w);
-}
-
-__global__ void __launch_bounds__(256)
-k_logscale(float4 *dst, const float4 *src, float k1, float k2) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = src[i];
-    float ls = fmaxf(0.0f, k1 * logf(1.0f + p.w * k2) / p.w);
-    dst[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
-}
-
-__global__ void __launch_bounds__(256)
-k_logencode(float4 *dst, const float4 *src, float degamma) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = src[i];
-    p.x = log2f(powf(p.x, degamma)) / 12.0f + 1.0f;
-    p.y = log2f(powf(p.y, degamma)) / 12.0f + 1.0f;
-    p.z = log2f(powf(p.z, degamma)) / 12.0f + 1.0f;
-    p.w = log2f(powf(p.w, degamma)) / 12.0f + 1.0f;
-    dst[i] = p;
-}
-
-__global__ void __launch_bounds__(256)
-k_apply_gamma(float *dst, const float4 *src, float gamma) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    dst[i] = powf(src[i].x, gamma);
-}
-
-__global__ void __launch_bounds__(256)
-k_haloclip(float4 *pix, const float *den, float gamma_m_1) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = pix[i];
-    float area = den[i];
-    if (p.w <= 0.0f) {
-        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
+k_map4(float4 *dst, const float4 *src, int n, Op op) {
+    const int base = blockIdx.x * (256 * PW_PER) + threadIdx.x;
+    float4 v[PW_PER];
+#pragma unroll
+    for (int k = 0; k < PW_PER; k++) {
+        int i = base + k * 256;
+        if (i < n) v[k] = src[op.index(i)];
     }
-    float ls = powf(p.w, gamma_m_1) / fmaxf(1.0f, area);
-    pix[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+#pragma unroll
+    for (int k = 0; k < PW_PER; k++) {
+        int i = base + k * 256;
+        if (i < n) dst[i] = op(v[k]);
+    }
 }
 
+// second input T2 (float or float4) read at the same index
+template <typename Op, typename T2>
 __global__ void __launch_bounds__(256)
-k_apply_gamma_full_hi(float4 *dst, const float4 *src, float gamma_m_1) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = src[i];
-    float ls = 0.0f;
-    if (p.w > 0.0f) ls = fmaxf(0.0f, p.w - 1.0f) / p.w;
-    dst[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
+k_map4x2(float4 *dst, const float4 *src, const T2 *src2, int n, Op op) {
+    const int base = blockIdx.x * (256 * PW_PER) + threadIdx.x;
+    float4 v[PW_PER];
+    T2 w[PW_PER];
+#pragma unroll
+    for (int k = 0; k < PW_PER; k++) {
+        int i = base + k * 256;
+        if (i < n) { v[k] = src[i]; w[k] = src2[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < PW_PER; k++) {
+        int i = base + k * 256;
+        if (i < n) dst[i] = op(v[k], w[k]);
+    }
 }
+
+// float4 in, one float out
+template <typename Op>
+__global__ void __launch_bounds__(256)
+k_map4to1(float *dst, const float4 *src, int n, Op op) {
+    const int base = blockIdx.x * (256 * PW_PER) + threadIdx.x;
+    float4 v[PW_PER];
+#pragma unroll
+    for (int k = 0; k < PW_PER; k++) {
+        int i = base + k * 256;
+        if (i < n) v[k] = src[i];
+    }
+#pragma unroll
+    for (int k = 0; k < PW_PER; k++) {
+        int i = base + k * 256;
+        if (i < n) dst[i] = op(v[k]);
+    }
+}
+
+struct op_base { __device__ __forceinline__ int index(int i) const { return i; } };
+
+__device__ __forceinline__ float4 scaled(float4 p, float s) {
+    return make_float4(p.x * s, p.y * s, p.z * s, p.w * s);
+}
+
+// Inverse of the slice-balancing accumulation layout (device/iter_kernel.cuh).
+struct op_unswizzle {
+    int swizzle_bins;
+    __device__ __forceinline__ int index(int i) const {
+        unsigned int u = (unsigned int)i;
+        unsigned int j = (u & 0xffff0000u) | ((u * 40503u) & 0xffffu);
+        return i < swizzle_bins ? (int)j : i;
+    }
+    __device__ __forceinline__ float4 operator()(float4 p) const { return p; }
+};
+
+// yuvo2rgb (code/color.py:33-40): remove the +0.5 per-sample chroma bias, then JPEG
+// full-range YUV -> RGB, clamped at 0; the density channel is kept.
+struct op_yuv_to_rgb : op_base {
+    __device__ __forceinline__ float4 operator()(float4 p) const {
+        float u = p.y - 0.5f * p.w, v = p.z - 0.5f * p.w;
+        float r = p.x + 1.402f * v;
+        float g = p.x - 0.34414f * u - 0.71414f * v;
+        float b = p.x + 1.772f * u;
+        return make_float4(fmaxf(0.0f, r), fmaxf(0.0f, g), fmaxf(0.0f, b), p.w);
+    }
+};
+
+struct op_logscale : op_base {
+    float k1, k2;
+    __device__ __forceinline__ float4 operator()(float4 p) const {
+        return scaled(p, fmaxf(0.0f, k1 * logf(1.0f + p.w * k2) / p.w));
+    }
+};
+
+struct op_logencode : op_base {
+    float degamma;
+    __device__ __forceinline__ float enc(float x) const {
+        return log2f(powf(x, degamma)) / 12.0f + 1.0f;
+    }
+    __device__ __forceinline__ float4 operator()(float4 p) const {
+        return make_float4(enc(p.x), enc(p.y), enc(p.z), enc(p.w));
+    }
+};
+
+struct op_apply_gamma : op_base {
+    float gamma;
+    __device__ __forceinline__ float operator()(float4 p) const { return powf(p.x, gamma); }
+};
+
+struct op_haloclip : op_base {
+    float gamma_m_1;
+    __device__ __forceinline__ float4 operator()(float4 p, float area) const {
+        if (p.w <= 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return scaled(p, powf(p.w, gamma_m_1) / fmaxf(1.0f, area));
+    }
+};
+
+struct op_gamma_full_hi : op_base {
+    __device__ __forceinline__ float4 operator()(float4 p) const {
+        float ls = 0.0f;
+        if (p.w > 0.0f) ls = fmaxf(0.0f, p.w - 1.0f) / p.w;
+        return scaled(p, ls);
+    }
+};
 
 __device__ __forceinline__ float gamma_toe(float w, float gamma_m_1, float linrange,
                                            float lingam) {
@@ -128,76 +188,61 @@ __device__ __forceinline__ float gamma_toe(float w, float gamma_m_1, float linra
     return ls;
 }
 
-__global__ void __launch_bounds__(256)
-k_smearclip(float4 *pix, const float4 *smear, float gamma_m_1, float linrange,
-            float lingam) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = pix[i], a = smear[i];
-    p.x += a.x; p.y += a.y; p.z += a.z; p.w += a.w;
-    if (p.w <= 0.0f) {
-        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
+struct op_smearclip : op_base {
+    float gamma_m_1, linrange, lingam;
+    __device__ __forceinline__ float4 operator()(float4 p, float4 a) const {
+        p.x += a.x; p.y += a.y; p.z += a.z; p.w += a.w;
+        if (p.w <= 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return scaled(p, gamma_toe(p.w, gamma_m_1, linrange, lingam));
     }
-    float ls = gamma_toe(p.w, gamma_m_1, linrange, lingam);
-    pix[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
-}
+};
 
-__global__ void __launch_bounds__(256)
-k_plainclip(float4 *pix, float gamma_m_1, float linrange, float lingam,
-            float brightness) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = pix[i];
-    if (p.w <= 0.0f) {
-        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
+struct op_plainclip : op_base {
+    float gamma_m_1, linrange, lingam, brightness;
+    __device__ __forceinline__ float4 operator()(float4 p) const {
+        if (p.w <= 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return scaled(p, gamma_toe(p.w, gamma_m_1, linrange, lingam) * brightness);
     }
-    float ls = gamma_toe(p.w, gamma_m_1, linrange, lingam) * brightness;
-    pix[i] = make_float4(p.x * ls, p.y * ls, p.z * ls, p.w * ls);
-}
+};
 
 // flam3-style gamma / vibrancy / highlight-power clip (code/filters.py:354-412)
-__global__ void __launch_bounds__(256)
-k_colorclip(float4 *pix, float vibrance, float highpow, float gamma,
-            float linrange, float lingam) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    float4 p = pix[i];
-    if (p.w <= 0.0f) {
-        pix[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
-    }
-    float4 o = p;
-    float alpha = powf(p.w, gamma);
-    if (p.w < linrange) {
-        float frac = p.w / linrange;
-        alpha = (1.0f - frac) * p.w * lingam + frac * alpha;
-    }
-    float ls = vibrance * alpha / p.w;
-    alpha = fminf(1.0f, fmaxf(0.0f, alpha));
-
-    float maxc = fmaxf(p.x, fmaxf(p.y, p.z));
-    float maxa = maxc * ls;
-    float newls = 1.0f / maxc;
-
-    if (maxa > 1.0f && highpow >= 0.0f) {
-        // desaturate towards white in proportion to the overshoot
-        float lsratio = powf(newls / ls, highpow);
-        p.x = maxc - (maxc - p.x * newls) * lsratio;
-        p.y = maxc - (maxc - p.y * newls) * lsratio;
-        p.z = maxc - (maxc - p.z * newls) * lsratio;
-    } else {
-        float adjhlp = -highpow;
-        if (adjhlp > 1.0f || maxa <= 1.0f) adjhlp = 1.0f;
-        if (maxc > 0.0f) {
-            float adj = (1.0f - adjhlp) * newls + adjhlp * ls;
-            p.x *= adj; p.y *= adj; p.z *= adj;
+struct op_colorclip : op_base {
+    float vibrance, highpow, gamma, linrange, lingam;
+    __device__ __forceinline__ float4 operator()(float4 p) const {
+        if (p.w <= 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 o = p;
+        float alpha = powf(p.w, gamma);
+        if (p.w < linrange) {
+            float frac = p.w / linrange;
+            alpha = (1.0f - frac) * p.w * lingam + frac * alpha;
         }
+        float ls = vibrance * alpha / p.w;
+        alpha = fminf(1.0f, fmaxf(0.0f, alpha));
+
+        float maxc = fmaxf(p.x, fmaxf(p.y, p.z));
+        float maxa = maxc * ls;
+        float newls = 1.0f / maxc;
+        if (maxa > 1.0f && highpow >= 0.0f) {
+            // desaturate towards white in proportion to the overshoot
+            float lsratio = powf(newls / ls, highpow);
+            p.x = maxc - (maxc - p.x * newls) * lsratio;
+            p.y = maxc - (maxc - p.y * newls) * lsratio;
+            p.z = maxc - (maxc - p.z * newls) * lsratio;
+        } else {
+            float adjhlp = -highpow;
+            if (adjhlp > 1.0f || maxa <= 1.0f) adjhlp = 1.0f;
+            if (maxc > 0.0f) {
+                float adj = (1.0f - adjhlp) * newls + adjhlp * ls;
+                p.x *= adj; p.y *= adj; p.z *= adj;
+            }
+        }
+        float rest = 1.0f - vibrance;
+        p.x += rest * powf(o.x, gamma);
+        p.y += rest * powf(o.y, gamma);
+        p.z += rest * powf(o.z, gamma);
+        return make_float4(fminf(1.0f, p.x), fminf(1.0f, p.y), fminf(1.0f, p.z), alpha);
     }
-    float rest = 1.0f - vibrance;
-    p.x += rest * powf(o.x, gamma);
-    p.y += rest * powf(o.y, gamma);
-    p.z += rest * powf(o.z, gamma);
-    pix[i] = make_float4(fminf(1.0f, p.x), fminf(1.0f, p.y), fminf(1.0f, p.z), alpha);
-}
+};
 
 // ---- 7-tap directional blurs ----------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -344,23 +389,17 @@ k_bilat_prep2(float2 *side, const float2 *aux, int pattern, coefs7 k, cb_dims di
     side[gi] = make_float2(1.0f / (den + 1.0e-6f), aux[gi].y);
 }
 
-__global__ void __launch_bounds__(256)
-k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern,
-                 int radius, float sstd, float cstd, float dstd, float gspeed,
-                 cb_dims dim) {
+// RADIUS > 0: compile-time radius (the loop unrolls); RADIUS == 0: run-time radius.
+// INTERIOR: every tap of every pixel of the block is inside the grid, so taps are
+// addressed with precomputed linear offsets and no clamping.
+template <int RADIUS, bool INTERIOR>
+__device__ __forceinline__ void bilateral_fast_body(
+        float4 *dst, const float4 *src, const float2 *side, int pattern, int radius_rt,
+        float cscale2, float dscale, float gspeed, const float *lspa, const int2 *offs,
+        const int *loffs, cb_dims dim) {
     PIX_XY();
-    __shared__ float lspa[32];
-    __shared__ int2 offs[36];
-    const float log2e = 1.44269502162933f;
-    if (threadIdx.y == 0) {
-        float df = (float)threadIdx.x;
-        lspa[threadIdx.x] = log2e * df * df / (-K_SQRT2 * sstd);
-    }
-    if (threadIdx.y == 1 && (int)threadIdx.x <= 2 * radius + 2)
-        offs[threadIdx.x] = shear_offset(pattern, (float)((int)threadIdx.x - radius - 1));
+    const int radius = RADIUS > 0 ? RADIUS : radius_rt;
     const int W = dim.astride, H = dim.aheight;
-    const float cscale2 = log2e / (-K_SQRT2 * 3.0f * cstd);
-    const float dscale = -0.5f / dstd;
 
     float4 cen = src[gi];
     float cpow = side[gi].y;
@@ -370,21 +409,23 @@ k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern
 
     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float wsum = 0.0f;
-    __syncthreads();
 
-    int2 o = offs[0];
-    float4 pix = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
-    o = offs[1];
-    int ni = clamp_idx(xi + o.x, yi + o.y, W, H);
+    auto tap = [&](int k) -> int {
+        if (INTERIOR) return gi + loffs[k];
+        int2 o = offs[k];
+        return clamp_idx(xi + o.x, yi + o.y, W, H);
+    };
+    float4 pix = src[tap(0)];
+    int ni = tap(1);
     float4 next = src[ni];
     float2 nside = side[ni];
 
+#pragma unroll
     for (int r = -radius; r <= radius; r++) {
         float prev = pix.w;
         pix = next;
         float2 ps = nside;
-        o = offs[r + radius + 2];
-        ni = clamp_idx(xi + o.x, yi + o.y, W, H);
+        ni = tap(r + radius + 2);
         next = src[ni];
         nside = side[ni];
 
@@ -396,7 +437,7 @@ k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern
             float vd = pix.z * pdrcp - cen.z;
             cdiff = yd * yd + ud * ud + vd * vd;
         }
-        float e = lspa[abs(r)] + cscale2 * cdiff + dscale * fabsf(cpow - ps.y);
+        float e = lspa[r < 0 ? -r : r] + cscale2 * cdiff + dscale * fabsf(cpow - ps.y);
         if (r != 0) {
             float grad = (next.w - prev) * ps.x;
             if (r < 0) grad = -grad;
@@ -413,6 +454,42 @@ k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern
     dst[gi] = make_float4(acc.x * rcp, acc.y * rcp, acc.z * rcp, acc.w * rcp);
 }
 
+template <int RADIUS>
+__global__ void __launch_bounds__(256)
+k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern,
+                 int radius_rt, float sstd, float cstd, float dstd, float gspeed,
+                 cb_dims dim) {
+    __shared__ float lspa[32];
+    __shared__ int2 offs[36];
+    __shared__ int loffs[36];
+    const float log2e = 1.44269502162933f;
+    const int radius = RADIUS > 0 ? RADIUS : radius_rt;
+    if (threadIdx.y == 0) {
+        float df = (float)threadIdx.x;
+        lspa[threadIdx.x] = log2e * df * df / (-K_SQRT2 * sstd);
+    }
+    // tap k is the pixel (k - radius - 1) steps along the direction, k = 0 .. 2*radius+2
+    for (int k = threadIdx.y * 32 + threadIdx.x; k <= 2 * radius + 2; k += 256) {
+        int2 o = shear_offset(pattern, (float)(k - radius - 1));
+        offs[k] = o;
+        loffs[k] = o.y * dim.astride + o.x;
+    }
+    __syncthreads();
+    const float cscale2 = log2e / (-K_SQRT2 * 3.0f * cstd);
+    const float dscale = -0.5f / dstd;
+    // reach of the farthest tap (|dir| <= 1 per axis, radius + 1 steps)
+    const int reach = radius + 1;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const bool interior = x0 - reach >= 0 && x0 + 31 + reach < dim.astride &&
+                          y0 - reach >= 0 && y0 + 7 + reach < dim.aheight;
+    if (interior)
+        bilateral_fast_body<RADIUS, true>(dst, src, side, pattern, radius_rt, cscale2, dscale,
+                                          gspeed, lspa, offs, loffs, dim);
+    else
+        bilateral_fast_body<RADIUS, false>(dst, src, side, pattern, radius_rt, cscale2, dscale,
+                                           gspeed, lspa, offs, loffs, dim);
+}
+
 // ---- C ABI -------------------------------------------------------------------
 static inline int nbins(const cb_dims *d) { return d->aheight * d->astride; }
 static inline dim3 grid2(const cb_dims *d) { return dim3(d->astride / 32, d->aheight / 8); }
@@ -422,12 +499,18 @@ static inline dim3 grid2(const cb_dims *d) { return dim3(d->astride / 32, d->ahe
                (d)->aheight > 0 && (d)->aheight % 16 == 0,                     \
                "dims must come from cb_calc_dim")
 
-#define POINTWISE(kernel, ...)                                                 \
-    do {                                                                       \
-        CHECK_DIM(dim);                                                        \
-        kernel<<<nbins(dim) / 256, 256, 0, cb_cs(s)>>>(__VA_ARGS__);           \
-        CB_LAUNCH_CHECK();                                                     \
-        return CB_OK;                                                          \
+static inline int pw_grid(const cb_dims *d) {
+    return (nbins(d) + 256 * PW_PER - 1) / (256 * PW_PER);
+}
+
+#define MAP4(dst, src, op)                                                        \
+    do {                                                                          \
+        CHECK_DIM(dim);                                                           \
+        k_map4<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(cb_ptr<float4>(dst),           \
+                                                   cb_ptr<const float4>(src),     \
+                                                   nbins(dim), op);               \
+        CB_LAUNCH_CHECK();                                                        \
+        return CB_OK;                                                             \
     } while (0)
 
 extern "C" {
@@ -436,54 +519,82 @@ int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins, const cb_dim
                       cb_stream s) {
     CB_REQUIRE(swizzle_bins >= 0 && swizzle_bins % 65536 == 0, "swizzle_bins must be a multiple of 65536");
     CB_REQUIRE(dim && swizzle_bins <= dim->aheight * dim->astride, "swizzle_bins exceeds the grid");
-    POINTWISE(k_hist_unswizzle, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), swizzle_bins);
+    op_unswizzle op;
+    op.swizzle_bins = swizzle_bins;
+    MAP4(dst4, src4, op);
 }
 
 int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s) {
-    POINTWISE(k_yuv_to_rgb, cb_ptr<float4>(dst), cb_ptr<const float4>(src));
+    MAP4(dst, src, op_yuv_to_rgb());
 }
 
 int cb_logscale(cb_dptr dst4, cb_dptr src4, float k1, float k2, const cb_dims *dim,
                 cb_stream s) {
-    POINTWISE(k_logscale, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), k1, k2);
+    op_logscale op;
+    op.k1 = k1; op.k2 = k2;
+    MAP4(dst4, src4, op);
 }
 
 int cb_logencode(cb_dptr dst4, cb_dptr src4, float degamma, const cb_dims *dim,
                  cb_stream s) {
-    POINTWISE(k_logencode, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), degamma);
+    op_logencode op;
+    op.degamma = degamma;
+    MAP4(dst4, src4, op);
 }
 
 int cb_apply_gamma(cb_dptr dst1, cb_dptr src4, float gamma, const cb_dims *dim,
                    cb_stream s) {
-    POINTWISE(k_apply_gamma, cb_ptr<float>(dst1), cb_ptr<const float4>(src4), gamma);
+    CHECK_DIM(dim);
+    op_apply_gamma op;
+    op.gamma = gamma;
+    k_map4to1<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(cb_ptr<float>(dst1),
+                                                  cb_ptr<const float4>(src4), nbins(dim), op);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int cb_haloclip(cb_dptr pix4, cb_dptr den1, float gamma_m_1, const cb_dims *dim,
                 cb_stream s) {
-    POINTWISE(k_haloclip, cb_ptr<float4>(pix4), cb_ptr<const float>(den1), gamma_m_1);
+    CHECK_DIM(dim);
+    op_haloclip op;
+    op.gamma_m_1 = gamma_m_1;
+    k_map4x2<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(cb_ptr<float4>(pix4), cb_ptr<const float4>(pix4),
+                                                 cb_ptr<const float>(den1), nbins(dim), op);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int cb_apply_gamma_full_hi(cb_dptr dst4, cb_dptr src4, float gamma_m_1,
                            const cb_dims *dim, cb_stream s) {
-    POINTWISE(k_apply_gamma_full_hi, cb_ptr<float4>(dst4), cb_ptr<const float4>(src4),
-              gamma_m_1);
+    (void)gamma_m_1;        // unused by the reference kernel too (code/filters.py:294-303)
+    MAP4(dst4, src4, op_gamma_full_hi());
 }
 
 int cb_smearclip(cb_dptr pix4, cb_dptr smear4, float gamma_m_1, float linrange,
                  float lingam, const cb_dims *dim, cb_stream s) {
-    POINTWISE(k_smearclip, cb_ptr<float4>(pix4), cb_ptr<const float4>(smear4),
-              gamma_m_1, linrange, lingam);
+    CHECK_DIM(dim);
+    op_smearclip op;
+    op.gamma_m_1 = gamma_m_1; op.linrange = linrange; op.lingam = lingam;
+    k_map4x2<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(cb_ptr<float4>(pix4), cb_ptr<const float4>(pix4),
+                                                 cb_ptr<const float4>(smear4), nbins(dim), op);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int cb_plainclip(cb_dptr pix4, float gamma_m_1, float linrange, float lingam,
                  float brightness, const cb_dims *dim, cb_stream s) {
-    POINTWISE(k_plainclip, cb_ptr<float4>(pix4), gamma_m_1, linrange, lingam, brightness);
+    op_plainclip op;
+    op.gamma_m_1 = gamma_m_1; op.linrange = linrange; op.lingam = lingam;
+    op.brightness = brightness;
+    MAP4(pix4, pix4, op);
 }
 
 int cb_colorclip(cb_dptr pix4, float vibrance, float highpow, float gamma,
                  float linrange, float lingam, const cb_dims *dim, cb_stream s) {
-    POINTWISE(k_colorclip, cb_ptr<float4>(pix4), vibrance, highpow, gamma, linrange,
-              lingam);
+    op_colorclip op;
+    op.vibrance = vibrance; op.highpow = highpow; op.gamma = gamma;
+    op.linrange = linrange; op.lingam = lingam;
+    MAP4(pix4, pix4, op);
 }
 
 static coefs7 load_coefs(const float c[7]) {
@@ -557,9 +668,14 @@ int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4, int pat
     CB_LAUNCH_CHECK();
     k_bilat_prep2<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
     CB_LAUNCH_CHECK();
-    k_bilateral_fast<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
-        cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
-        cstd, dstd, gspeed, *dim);
+    if (radius == 15)       // the reference's fixed radius (cuburn/filters.py:59): unrolled
+        k_bilateral_fast<15><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+            cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
+            cstd, dstd, gspeed, *dim);
+    else
+        k_bilateral_fast<0><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+            cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
+            cstd, dstd, gspeed, *dim);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

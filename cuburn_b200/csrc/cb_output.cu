@@ -32,6 +32,8 @@ __device__ __forceinline__ float jpeg_cr(float4 p) {
     return FS(FS(FM(0.5f, p.x), FM(0.418688f, p.y)), FM(0.081312f, p.z));
 }
 
+#define CV_BATCH 4
+
 template <int FMT>
 __global__ void __launch_bounds__(256)
 k_convert(void *dstv, const float4 *src, int gutter, cb_dims dim, mwc_st *seeds,
@@ -42,9 +44,24 @@ k_convert(void *dstv, const float4 *src, int gutter, cb_dims dim, mwc_st *seeds,
     const int w = dim.width, h = dim.height;
     const int npix = w * h;
 
-    for (int i = sid; i < npix; i += nstreams) {
+    // A stream's pixels are produced in order (its RNG state is carried along), but
+    // their loads are independent: fetch CV_BATCH of them before converting any.
+    for (int i0 = sid; i0 < npix; i0 += CV_BATCH * nstreams) {
+      float4 batch[CV_BATCH];
+#pragma unroll
+      for (int k = 0; k < CV_BATCH; k++) {
+          int i = i0 + k * nstreams;
+          if (i < npix) {
+              int y = i / w, x = i - y * w;
+              batch[k] = src[(y + gutter) * dim.astride + x + gutter];
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < CV_BATCH; k++) {
+        int i = i0 + k * nstreams;
+        if (i >= npix) break;
         int y = i / w, x = i - y * w;
-        float4 p = src[(y + gutter) * dim.astride + x + gutter];
+        float4 p = batch[k];
         if (FMT == CB_FMT_RGBA_U8) {
             uchar4 o;
             o.x = (unsigned char)dither_clamp(rng, 255.0f, p.x);
@@ -100,6 +117,7 @@ k_convert(void *dstv, const float4 *src, int gutter, cb_dims dim, mwc_st *seeds,
             d[i + npix] = (unsigned short)FA(dither_clamp(rng, 3584.0f, cb), 256.0f);
             d[i + 2 * npix] = (unsigned short)FA(dither_clamp(rng, 3584.0f, cr), 256.0f);
         }
+      }
     }
     seeds[sid] = rng;
 }
