@@ -234,6 +234,8 @@ class RenderManager(object):
         self.info_a, self.info_b = DevInfo(), DevInfo()
         self.stream_a, self.stream_b = N.Stream(), N.Stream()
         self.filt_evt = self.copy_evt = None
+        import collections
+        self._pinned = collections.deque(maxlen=4)
         # share of the frame's samples this manager renders (multi-GPU stills)
         self.sample_share = (rank, world)
         self.hist_hook = None
@@ -270,7 +272,9 @@ class RenderManager(object):
         prog[:] = pk.program_array()
         N.memcpy_htod(src.d_row_mag, mag, s)
         N.memcpy_htod(src.d_program, prog, s)
-        self._pinned = (times, knots, palettes, palette_times, mag, prog)
+        # keep the staging arrays of the last few frames alive: their async H2D copies
+        # may still be queued behind earlier frames on the alternating streams
+        self._pinned.append((times, knots, palettes, palette_times, mag, prog))
 
     # -- interpolate -------------------------------------------------------------
     def _interp(self, rdr, gnm, dim, ts, td):

@@ -278,3 +278,109 @@ def test_rng_streams_and_points_persist(native, built):
     assert np.array_equal(s3, s1)
     # same sample set => same counts (count adds are exact in float32)
     assert np.array_equal(h3[..., 3], h1[..., 3])
+
+
+def _hist_for(N, gnm, w, h, spp, tc=None, frame_width=0, seed=21):
+    from cuburn_b200 import render, profile
+    prof = dict(width=w, height=h, spp=spp, frame_width=frame_width, fps=24, duration=1.0)
+    if tc is None:
+        prof.update(start=1, end=2)
+    gprof = profile.wrap(prof, gnm)
+    tc = profile.enumerate_times(gprof)[0][1][0] if tc is None else tc
+    ts, td = frame_window(gprof, tc)
+    rmgr = render.RenderManager(seed=seed)
+    rdr = render.Renderer(gnm, gprof)
+    dim = rmgr.fb.set_dim(w, h)
+    rmgr._copy(rdr, gnm)
+    rmgr._interp(rdr, gnm, dim, ts, td)
+    rmgr._iter(rdr, gnm, gprof, dim, tc)
+    rmgr.stream_a.synchronize()
+    hist = N.from_device(rmgr.fb.d_front, (dim.ah, dim.astride, 4), np.float32)
+    return hist, rmgr.last_iter_samples, ts, td, tc
+
+
+def test_density_parity_with_motion_blur(native, built):
+    """T8 across a wide shutter: 1024 distinct parameter blocks and 64 palette rows
+    (shared-memory parameter variant) vs the oracle's temporal sampling."""
+    N = native
+    from cuburn_b200 import samples, mwc
+    from oracle import flame_ref as R
+    gnm = samples.g6f(animated=True)
+    gnm['palette'] = [[0.0] + samples.make_palette('spectrum'), [1.0] + samples.make_palette('fire')]
+    w, h, spp = 320, 180, 600
+    hist, n, ts, td, tc = _hist_for(N, gnm, w, h, spp, tc=0.4, frame_width=4.0)
+    assert td > 0.1
+    ev = R.GenomeEval(gnm, w, h, tc, td)
+    seeds = mwc.make_seeds(32768, host_seed=5)
+    pal, seeds = R.palette_table(gnm, ts, td, seeds)
+    ohist, _ = R.iterate(ev, pal, seeds, n)
+    fa, fb = hist[..., 3].sum() / n, ohist[..., 3].sum() / n
+    assert abs(fa - fb) < 2e-3
+    pa, pb = pool8(hist[..., 3]), pool8(ohist[..., 3])
+    m = (pa + pb) > 400
+    z = (pa - pb)[m] / np.sqrt((pa + pb)[m])
+    assert m.sum() > 100 and abs(z.mean()) < 0.3 and z.std() < 2.0, (z.mean(), z.std())
+    for ch in range(3):
+        ca, cb = pool8(hist[..., ch]), pool8(ohist[..., ch])
+        assert np.abs(ca[m] / pa[m] - cb[m] / pb[m]).mean() < 0.01
+
+
+def test_edge_cases_do_not_break_the_kernel(native, built):
+    """Single xform, tiny frames, fewer samples than one round, a divergent genome."""
+    N = native
+    from cuburn_b200 import samples
+    # one xform: no density slots, the choice chain is a single call
+    g1 = samples.g3()
+    g1['xforms'] = {'7': g1['xforms']['1']}
+    hist, n, *_ = _hist_for(N, g1, 64, 32, 50)
+    assert n == 64 * 32 * 50 and np.isfinite(hist).all() and hist[..., 3].sum() > 0
+    # tiny frame, ragged size, fewer samples than one 256-thread round
+    hist, n, *_ = _hist_for(N, samples.g3(), 17, 9, 1)
+    assert n == 153 and np.isfinite(hist).all() and 0 < hist[..., 3].sum() <= 153
+    # divergent: expanding affines blow every trajectory up; points are re-seeded, nothing hangs
+    g2 = samples.g3()
+    for xf in g2['xforms'].values():
+        xf['pre_affine']['magnitude'] = {'x': 40.0, 'y': 40.0}
+        xf['variations'] = {'exponential': {'weight': 1.0}, 'linear': {'weight': 1.0}}
+    hist, n, *_ = _hist_for(N, g2, 64, 32, 20)
+    assert np.isfinite(hist).all() and hist.min() >= 0
+    # zero-weight xform is never chosen
+    g3 = samples.g3()
+    g3['xforms']['2']['weight'] = 0
+    g3['xforms']['2']['color'] = 1.0
+    g3['xforms']['0']['color'] = 0.0
+    g3['xforms']['1']['color'] = 0.0
+    hist, n, *_ = _hist_for(N, g3, 64, 32, 50)
+    assert hist[..., 3].sum() > 0
+
+
+def test_max_knots_and_palettes(native, built):
+    """32 knots per spline and 32 palettes are the packed limits (render.py:178-184)."""
+    N = native
+    from cuburn_b200 import samples
+    from oracle import flame_ref as R
+    from helpers import bits
+    g = samples.g3()
+    knots = [0.0, 0.0, 20.0, 0.0]
+    for i in range(28):
+        knots += [(i + 1) / 29.0, float((i * 7) % 11)]
+    g['camera']['rotation'] = knots                       # 2 + 28 + 2 guards = 32 knots
+    g['palette'] = [[i / 31.0] + samples.make_palette(('fire', 'ocean', 'spectrum')[i % 3])
+                    for i in range(32)]
+    from cuburn_b200 import render, profile
+    gprof = profile.wrap(dict(width=64, height=32, spp=20, frame_width=24.0, fps=24, duration=1.0), g)
+    rmgr = render.RenderManager(seed=2)
+    rdr = render.Renderer(g, gprof)
+    dim = rmgr.fb.set_dim(64, 32)
+    rmgr._copy(rdr, g)
+    rmgr._interp(rdr, g, dim, 0.0, 1.0)
+    rmgr.stream_a.synchronize()
+    params = N.from_device(rmgr.info_a.d_params, (1024, rdr.packer.param_stride), np.float32)
+    ev = R.GenomeEval(g, 64, 32, 0.5, 1.0)
+    for c in ('xx', 'xy', 'xo', 'yx', 'yy', 'yo'):
+        i = rdr.packer.slot('camera', c)
+        assert np.array_equal(bits(params[:, i]), bits(ev.values['camera.' + c])), c
+    pal = N.from_device(rmgr.info_a.d_palette, (64, 256, 4), np.float32)
+    from cuburn_b200 import mwc
+    opal, _ = R.palette_table(g, 0.0, 1.0, mwc.make_seeds(262144, host_seed=2))
+    assert np.array_equal(pal, opal)
