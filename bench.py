@@ -33,7 +33,16 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-CONFIG = dict(genome='G6F', width=1920, height=1080, spp=2000)
+WORKLOADS = {
+    # BASELINE.json configs[1]: the default; weak-scaled (every GPU runs 2000 spp)
+    'still1080': dict(genome='G6F', width=1920, height=1080, spp=2000, scaling='weak',
+                      label='1080p still, G6F (6 xforms + final xform, 12 variation types), '
+                            '2000 spp per GPU'),
+    # BASELINE.json configs[2]: one 4K frame at 4000 spp split over the GPUs (strong)
+    'still4k': dict(genome='G6F', width=3840, height=2160, spp=4000, scaling='strong',
+                    label='3840x2160 still, G6F, 4000 spp in total, samples split over the GPUs'),
+}
+CONFIG = dict(WORKLOADS['still1080'])
 # profiles/r01_final_cb_iter.md: 33.9 MB read + 0.1 MB written per launch (the first
 # touch of the histogram; 66 GB of atomic payload stays in L2)
 NCU_DRAM_BYTES_PER_LAUNCH = 33.96e6
@@ -141,8 +150,9 @@ def measure_red_peak(N, hist_ptr, nbins, seeds_ptr, sms):
 def frame_setup(n_gpus, rank, seed=1):
     from cuburn_b200 import _native as N, samples, profile, render
     gnm = samples.GENOMES[CONFIG['genome']]()
+    spp = CONFIG['spp'] * (n_gpus if CONFIG['scaling'] == 'weak' else 1)
     prof = dict(width=CONFIG['width'], height=CONFIG['height'],
-                spp=CONFIG['spp'] * n_gpus, frame_width=0, start=1, end=2)
+                spp=spp, frame_width=0, start=1, end=2)
     gprof = profile.wrap(prof, gnm)
     tc = profile.enumerate_times(gprof)[0][1][0]
     rmgr = render.RenderManager(seed=seed, rank=rank, world=n_gpus)
@@ -204,7 +214,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='still1080', choices=sorted(WORKLOADS),
+                    help='still1080 = BASELINE configs[1] (default); still4k = configs[2]')
     args = ap.parse_args()
+    CONFIG.clear()
+    CONFIG.update(WORKLOADS[args.workload])
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
 
     if args.impl == 'reference':
@@ -357,10 +371,10 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        n_cpu = CONFIG['width'] * CONFIG['height'] * 500        # ~10-20 s of CPU work
+        n_cpu = 1920 * 1080 * 500                               # ~10-20 s of CPU work
         rate, cores = cpu_chaos_rate(n_cpu)
         cpu = {'value': rate, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d samples (1080p x 500 spp) of the same genome, chaos game only'
+               'sample': '%d samples (500 spp worth of a 1080p frame) of the same genome, chaos game only'
                          % n_cpu}
 
     # 3 interp + fill + iter + unswizzle + yuv + 8 x 3 bilateral + logscale + 6 smearclip + convert
@@ -368,11 +382,9 @@ def main():
     line = {
         'metric': 'ifs_iterations_per_second', 'value': value, 'unit': 'iterations/s',
         'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': CONFIG['scaling'],
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '1080p still, G6F (6 xforms + final xform, 12 variation '
-                               'types), %d spp per GPU, default filter chain, RGBA8 out'
-                               % CONFIG['spp'],
+        'config': {'workload': CONFIG['label'] + ', default filter chain, RGBA8 out',
                    'samples_per_step': total, 'frames_per_second': 1e3 / ms_per_step,
                    'l2': 'L2 flushed between timed steps (512 MiB fill)',
                    'timing': 'CUDA events on the launching stream, per step, max over ranks',
