@@ -43,9 +43,10 @@ WORKLOADS = {
                     label='3840x2160 still, G6F, 4000 spp in total, samples split over the GPUs'),
 }
 CONFIG = dict(WORKLOADS['still1080'])
-# profiles/r01_final_cb_iter.md: 33.9 MB read + 0.1 MB written per launch (the first
-# touch of the histogram; 66 GB of atomic payload stays in L2)
-NCU_DRAM_BYTES_PER_LAUNCH = 33.96e6
+# profiles/r01_final_cb_iter.md (ncu --set full, still1080 workload): 37.66 MB read +
+# 0.86 MB written per cb_iter launch -- the first touch of the histogram; the 66 GB of
+# atomic payload never leaves L2
+NCU_DRAM_BYTES_PER_LAUNCH = 38.5e6
 UNIT = 65536
 
 
