@@ -371,7 +371,7 @@ def main():
                         'ms': filt_ms}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and n_gpus == 1:      # rank 0 at N = 1 only
         n_cpu = 1920 * 1080 * 500                               # ~10-20 s of CPU work
         rate, cores = cpu_chaos_rate(n_cpu)
         cpu = {'value': rate, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',

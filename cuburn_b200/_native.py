@@ -14,7 +14,7 @@ from ctypes import (c_int, c_int32, c_uint32, c_uint64, c_size_t, c_float,
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libcuburn_b200.so')
+LIB_PATH = os.environ.get('CUBURN_B200_LIB') or os.path.join(HERE, 'csrc', 'libcuburn_b200.so')
 
 CB_OK = 0
 CB_ERR_CUDA, CB_ERR_NVRTC, CB_ERR_INVALID, CB_ERR_NOMEM = -1, -2, -3, -4

@@ -454,8 +454,11 @@ __device__ __forceinline__ void bilateral_fast_body(
     dst[gi] = make_float4(acc.x * rcp, acc.y * rcp, acc.z * rcp, acc.w * rcp);
 }
 
+#ifndef BILAT_MIN_CTAS
+#define BILAT_MIN_CTAS 4
+#endif
 template <int RADIUS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BILAT_MIN_CTAS)
 k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern,
                  int radius_rt, float sstd, float cstd, float dstd, float gspeed,
                  cb_dims dim) {

@@ -345,13 +345,27 @@ class RenderManager(object):
         self.last_iter_samples = n
 
     # -- frame -----------------------------------------------------------------------
-    def queue_frame(self, rdr, gnm, gprof, tc, copy=True):
+    def queue_frame(self, rdr, gnm, gprof, tc, copy=True, frame_seed=None):
         """
         Queue one frame; returns ``(evt, h_out)`` (render.py:374-434).  ``evt``
         completes when ``h_out`` (pinned host memory in the output module's
         format) is valid.  Not thread-safe.
+
+        ``frame_seed`` (an addition): re-seed every RNG stream for this frame, so a
+        frame's sample set does not depend on which frames were rendered before it
+        on this GPU -- what a frame-partitioned multi-GPU animation needs to be
+        reproducible.
         """
         timing_event = N.Event().record(self.stream_b)
+        if frame_seed is not None:
+            from . import mwc as _mwc
+            seeds = self.fb.pool.allocate((self.fb.nstreams, 3), 'u4')
+            seeds[:] = _mwc.make_seeds(self.fb.nstreams, host_seed=int(frame_seed))
+            # the seed table is shared with the previous frame (which ran on stream_b
+            # and still dithers its output from it): order this upload after it
+            self.stream_a.wait_for_event(N.Event().record(self.stream_b))
+            N.memcpy_htod(self.fb.d_seeds, seeds, self.stream_a)
+            self._pinned.append((seeds,))
         dim = self.fb.set_dim(gprof.width, gprof.height, self.stream_b)
 
         td = gprof.frame_width(tc) / round(gprof.fps * gprof.duration)
