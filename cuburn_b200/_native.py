@@ -59,7 +59,8 @@ class IterArgs(ctypes.Structure):
                 ('param_stride', c_int32), ('nts', c_int32),
                 ('pal_rows', c_int32), ('fuse_rounds', c_int32), ('swizzle_bins', c_int32),
                 ('first_sample', c_uint64), ('nsamples', c_uint64),
-                ('total_samples', c_uint64)]
+                ('total_samples', c_uint64), ('cells', c_uint64),
+                ('palette_packed', c_uint64)]
 
 
 _SIGNATURES = {
@@ -106,6 +107,8 @@ _SIGNATURES = {
                                  c_int, c_int, POINTER(c_void_p), c_void_p]),
     'cb_module_set_global': (c_int, [c_void_p, c_char_p, c_uint64, c_size_t, c_void_p]),
     'cb_iterate': (c_int, [c_void_p, POINTER(IterArgs), c_int, c_void_p]),
+    'cb_palette_pack': (c_int, [c_uint64, c_uint64, c_int, c_void_p]),
+    'cb_flush_packed': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_hist_unswizzle': (c_int, [c_uint64, c_uint64, c_int, POINTER(Dims), c_void_p]),
     'cb_yuv_to_rgb': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_den_blur': (c_int, [c_uint64, c_uint64, c_int, c_int, POINTER(c_float),

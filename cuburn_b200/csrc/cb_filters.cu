@@ -113,6 +113,29 @@ k_map4to1(float *dst, const float4 *src, int n, Op op) {
 
 struct op_base { __device__ __forceinline__ int index(int i) const { return i; } };
 
+// flush_atom (code/iter.py:420-479): add what is left in the packed u64 cells
+// (count:10 | Y:18 | U:18 | V:18 of 8-bit levels) into the float4 histogram.
+struct op_flush_packed : op_base {
+    __device__ __forceinline__ float4 operator()(float4 h, unsigned long long v) const {
+        const float k = 1.0f / 255.0f;
+        h.x += (float)(unsigned int)((v >> 36) & 0x3ffffull) * k;
+        h.y += (float)(unsigned int)((v >> 18) & 0x3ffffull) * k;
+        h.z += (float)(unsigned int)(v & 0x3ffffull) * k;
+        h.w += (float)(unsigned int)(v >> 54);
+        return h;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+k_palette_pack(unsigned long long *out, const float4 *pal, int n) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pal[i];      // exact 8-bit levels / 255 (cb_interp_palette)
+    unsigned long long y = __float2uint_rn(p.x * 255.0f), u = __float2uint_rn(p.y * 255.0f),
+                       v = __float2uint_rn(p.z * 255.0f);
+    out[i] = (1ull << 54) | (y << 36) | (u << 18) | v;
+}
+
 __device__ __forceinline__ float4 scaled(float4 p, float s) {
     return make_float4(p.x * s, p.y * s, p.z * s, p.w * s);
 }
@@ -517,6 +540,23 @@ static inline int pw_grid(const cb_dims *d) {
     } while (0)
 
 extern "C" {
+
+int cb_palette_pack(cb_dptr palette_packed, cb_dptr palette4, int nrows, cb_stream s) {
+    CB_REQUIRE(nrows > 0, "no palette rows");
+    k_palette_pack<<<nrows, 256, 0, cb_cs(s)>>>(cb_ptr<unsigned long long>(palette_packed),
+                                                cb_ptr<const float4>(palette4), nrows * 256);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    k_map4x2<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(
+        cb_ptr<float4>(hist4), cb_ptr<const float4>(hist4),
+        cb_ptr<const unsigned long long>(cells), nbins(dim), op_flush_packed());
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
 
 int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins, const cb_dims *dim,
                       cb_stream s) {

@@ -49,7 +49,13 @@ struct iter_args {
     unsigned long long first_sample;
     unsigned long long nsamples;
     unsigned long long total_samples;
+    unsigned long long *cells;                 // ACC_PACKED: u64 [aheight][astride]
+    const unsigned long long *palette_packed;  // ACC_PACKED: u64 [pal_rows][256]
 };
+
+#ifndef ACC_PACKED
+#define ACC_PACKED 0
+#endif
 
 #define ITER_WARPS (ITER_THREADS / 32)
 #define UNIT_SAMPLES (ITER_THREADS * UNIT_ROUNDS)
@@ -57,6 +63,35 @@ struct iter_args {
 __device__ __forceinline__ void red_add_f32x4(float4 *addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- packed accumulation (grids far larger than L2) ---------------------------------
+// The reference's cell format (cuburn/code/iter.py:334-407, interp.py:428-429): one
+// u64 per bin, count:10 | sum Y:18 | sum U:18 | sum V:18 of 8-bit palette levels, good
+// for 1023 samples.  Half the bytes per bin of the float4 histogram, so twice as many
+// bins stay L2-resident.  The reference lets 3 % of the warps check the returned count
+// and drain the cell once it has passed 512; between that check and the drain a hot
+// bin keeps filling (one L2 round trip, hundreds of adds at B200 rates), and a warp
+// that has converged onto one bin adds 32 at a time.  Here, in every round ONE lane of
+// each warp (rotating with the warp's random word) drains unconditionally: it swaps
+// the cell for zero and moves what it held, plus its own sample, into the float4
+// histogram.  Every bin is therefore drained after ~32 adds on average whatever its
+// rate; running past 1023 would take 1023 consecutive undrained adds, (31/32)^1023.
+// cb_flush_packed adds what is left in the cells at the end (flush_atom,
+// iter.py:420-479).
+__device__ __forceinline__ void accumulate_packed(unsigned long long *cell, float4 *hist,
+                                                  unsigned long long v, bool drain) {
+    if (!drain) {
+        asm volatile("red.global.add.u64 [%0], %1;" :: "l"(cell), "l"(v) : "memory");
+        return;
+    }
+    unsigned long long old = atomicExch(cell, 0ull);
+    float cnt = (float)((unsigned int)(old >> 54) + 1u);
+    float y = (float)((unsigned int)((old >> 36) & 0x3ffffull) + (unsigned int)((v >> 36) & 0xffull));
+    float u = (float)((unsigned int)((old >> 18) & 0x3ffffull) + (unsigned int)((v >> 18) & 0xffull));
+    float w = (float)((unsigned int)(old & 0x3ffffull) + (unsigned int)(v & 0xffull));
+    const float k = 1.0f / 255.0f;
+    red_add_f32x4(hist, make_float4(y * k, u * k, w * k, cnt));
 }
 
 __device__ __forceinline__ bool point_is_bad(float x, float y) {
@@ -126,15 +161,17 @@ __device__ __forceinline__ int exchange_slot(int tid, int warp, int lane, int ro
 
 // Apply one round of the chaos game to this thread's point and swap points
 // across the CTA.  `round` only steers the permutation.
-__device__ __forceinline__ void chaos_round(xchg_buf *xb, int tid, int warp, int lane,
-                                            int round, float &x, float &y, float &c,
-                                            mwc_st &rng) {
+__device__ __forceinline__ unsigned int chaos_round(xchg_buf *xb, int tid, int warp, int lane,
+                                                    int round, float &x, float &y, float &c,
+                                                    mwc_st &rng) {
     if (point_is_bad(x, y)) reseed_point(x, y, c, rng);
 
-    // one xform choice per warp per round (iter.py:197-201,261)
-    float sel = 0.0f;
-    if (lane == 0) sel = mwc_next_01(rng);
-    sel = __shfl_sync(0xffffffffu, sel, 0);
+    // one random word per warp per round (iter.py:197-201,261): its value picks the
+    // xform, its low bits decide whether this round checks for cell overflow
+    unsigned int word = 0;
+    if (lane == 0) word = mwc_next(rng);
+    word = __shfl_sync(0xffffffffu, word, 0);
+    float sel = __uint2float_rn(word) * 2.3283064365386962890625e-10f;
     chaos_step(sel, x, y, c, rng);
 
     xchg_buf *b = xb + (round & 1);
@@ -146,12 +183,17 @@ __device__ __forceinline__ void chaos_round(xchg_buf *xb, int tid, int warp, int
     x = p.x;
     y = p.y;
     c = b->c[tid];
+    return word;
 }
 
 extern "C" __global__ void __launch_bounds__(ITER_THREADS, ITER_MIN_CTAS)
 cb_iter(const __grid_constant__ iter_args a) {
     __shared__ xchg_buf xb[2];
+#if ACC_PACKED
+    __shared__ unsigned long long s_pal[256];
+#else
     __shared__ float4 s_pal[256];
+#endif
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -186,7 +228,11 @@ cb_iter(const __grid_constant__ iter_args a) {
             s_params[i] = a.params[(size_t)ts * a.param_stride + i];
 #endif
         if (row != cur_row) {
+#if ACC_PACKED
+            s_pal[tid] = a.palette_packed[row * 256 + tid];
+#else
             s_pal[tid] = a.palette[row * 256 + tid];
+#endif
             cur_row = row;
         }
         __syncthreads();
@@ -208,7 +254,7 @@ cb_iter(const __grid_constant__ iter_args a) {
         const float color_dither = 0.49f * mwc_next_11(rng);      // iter.py:185
 
         for (int r = 0; r < rounds; r++, round_ctr++) {
-            chaos_round(xb, tid, warp, lane, round_ctr, x, y, c, rng);
+            unsigned int word = chaos_round(xb, tid, warp, lane, round_ctr, x, y, c, rng);
             if (r * ITER_THREADS + tid >= live) continue;
 
             float fx = x, fy = y, fc = c;
@@ -217,8 +263,13 @@ cb_iter(const __grid_constant__ iter_args a) {
 #endif
             int bin = sample_bin(fx, fy, a.dim.astride, a.dim.aheight);
             if (bin < 0) continue;
+#if ACC_PACKED
+            accumulate_packed(a.cells + bin, a.hist + bin, s_pal[color_index(fc, color_dither)],
+                              (word & 31u) == (unsigned int)lane);
+#else
             float4 col = s_pal[color_index(fc, color_dither)];
             red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), col);
+#endif
         }
     }
 

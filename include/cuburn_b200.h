@@ -154,12 +154,24 @@ typedef struct {
     uint64_t first_sample;   /* global index of the first sample of this call */
     uint64_t nsamples;       /* samples (recorded xform applications) to run */
     uint64_t total_samples;  /* samples of the whole frame, all calls/GPUs */
+    cb_dptr cells;           /* packed-accumulator module only: u64 [aheight][astride]
+                                cells (count:10 | Y:18 | U:18 | V:18, iter.py:334-407) */
+    cb_dptr palette_packed;  /* packed-accumulator module only: u64 [pal_rows][256]
+                                from cb_palette_pack */
 } cb_iter_args;
 /* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
  * accumulated into hist.  grid_ctas persistent CTAs of 256 threads; work is
  * split in units of 16384 samples and first_sample must be unit aligned. */
 int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas,
                cb_stream s);
+
+/* Packed accumulation, for grids far larger than L2 (the reference's scheme,
+ * iter.py:334-544).  cb_palette_pack turns the float4 palette table into the u64
+ * addends ((1<<54) | Y<<36 | U<<18 | V, interp.py:428-429); the ACC_PACKED variant of
+ * the iterate module adds them into `cells` and spills full cells into `hist`;
+ * cb_flush_packed is flush_atom (iter.py:420-479): hist[i] += unpack(cells[i]). */
+int cb_palette_pack(cb_dptr palette_packed, cb_dptr palette4, int nrows, cb_stream s);
+int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream s);
 
 /* Undo the accumulation layout: dst[i] = src[swizzle(i)] for i < swizzle_bins,
  * dst[i] = src[i] above; dst is the linear float4 [aheight][astride] histogram the
