@@ -1,7 +1,9 @@
 """
-Genome look-up by file name or ID (reference cuburn/genome/db.py): a directory of
-``<id>.json`` files, or one JSON file holding many documents; ``get_anim`` turns
-whatever it finds (flam3 XML, node, edge, animation) into an animation.
+Genome look-up by file name or ID, and conversion of whatever is found into an
+animation.  Same surface as the reference module (cuburn/genome/db.py):
+``connect(path)`` -> ``GenomeDB`` with ``get / stash / get_anim``; ``OneFileDB``
+holds many documents in one JSON file, ``FilesystemDB`` is a directory of
+``<id>.json`` files.
 """
 import json
 import os
@@ -9,55 +11,85 @@ import warnings
 
 from . import convert
 
+_XML_EXTENSIONS = ('flam3', 'flame')
+_KNOWN_EXTENSIONS = _XML_EXTENSIONS + ('json',)
+
+
+def _split_name(name):
+    """'dir/spark.flam3' -> ('spark', 'flam3'); unknown extensions stay in the name."""
+    base = os.path.basename(name)
+    head, dot, ext = base.rpartition('.')
+    if dot and ext in _KNOWN_EXTENSIONS:
+        return head, ext
+    return base, ''
+
+
+def _load_xml(path):
+    with open(path) as fp:
+        flames = convert.XMLGenomeParser.parse(fp.read())
+    if len(flames) != 1:
+        warnings.warn('%d flames in file, only using one.' % len(flames))
+    return convert.flam3_to_node(flames[0])
+
 
 class GenomeDB(object):
+    """Base class: documents by ID, with an in-memory overlay (``stash``)."""
     def __init__(self):
         self.stashed = {}
 
     def _get(self, id):
         raise NotImplementedError()
 
-    def get(self, id):
-        if id in self.stashed:
-            return self.stashed[id]
-        return self._get(id)
-
     def stash(self, id, gnm):
         self.stashed[id] = gnm
 
-    def get_anim(self, name, half=False):
-        """``(animation dict, basename suitable for output files)``."""
-        basename = os.path.basename(name)
-        head, dot, ext = basename.rpartition('.')
-        if dot and ext in ('json', 'flam3', 'flame'):
-            basename = head
-        else:
-            ext = ext if dot else ''
+    def get(self, id):
+        try:
+            return self.stashed[id]
+        except KeyError:
+            return self._get(id)
 
-        if os.path.isfile(name) and ext in ('flam3', 'flame'):
-            with open(name) as fp:
-                flames = convert.XMLGenomeParser.parse(fp.read())
-            if len(flames) != 1:
-                warnings.warn('%d flames in file, only using one.' % len(flames))
-            gnm = convert.flam3_to_node(flames[0])
-        elif os.path.isfile(name) and ext == 'json':
-            with open(name) as fp:
-                gnm = json.load(fp)
-        else:
-            gnm = self.get(name)
+    def load(self, name):
+        """The raw document behind ``name``: a file on disk wins over a DB id."""
+        _, ext = _split_name(name)
+        if os.path.isfile(name):
+            if ext in _XML_EXTENSIONS:
+                return _load_xml(name)
+            if ext == 'json':
+                with open(name) as fp:
+                    return json.load(fp)
+        return self.get(name)
 
-        if gnm['type'] == 'node':
+    def to_anim(self, gnm, half=False):
+        kind = gnm['type']
+        if kind == 'node':
             gnm = convert.node_to_anim(self, gnm, half=half)
-        elif gnm['type'] == 'edge':
+        elif kind == 'edge':
             gnm = convert.edge_to_anim(self, gnm)
         assert gnm['type'] == 'animation', 'Unrecognized genome type.'
-        return gnm, basename
+        return gnm
+
+    def get_anim(self, name, half=False):
+        """``(animation dict, basename suitable for output files)`` (db.py:22-54)."""
+        return self.to_anim(self.load(name), half), _split_name(name)[0]
+
+
+class FilesystemDB(GenomeDB):
+    def __init__(self, path):
+        super().__init__()
+        self.path = path
+
+    def _get(self, id):
+        fname = id if id.endswith('.json') else id + '.json'
+        with open(os.path.join(self.path, fname)) as fp:
+            return json.load(fp)
 
 
 class OneFileDB(GenomeDB):
     def __init__(self, dct):
         super().__init__()
-        assert dct.get('type') == 'onefiledb', "Doesn't look like a OneFileDB."
+        if dct.get('type') != 'onefiledb':
+            raise AssertionError("Doesn't look like a OneFileDB.")
         self.dct = dct
 
     @classmethod
@@ -69,23 +101,11 @@ class OneFileDB(GenomeDB):
         return self.dct[id]
 
 
-class FilesystemDB(GenomeDB):
-    def __init__(self, path):
-        super().__init__()
-        self.path = path
-
-    def _get(self, id):
-        if not id.endswith('.json'):
-            id += '.json'
-        with open(os.path.join(self.path, id)) as fp:
-            return json.load(fp)
-
-
 def connect(path):
-    if os.path.isfile(path):
-        try:
-            return OneFileDB.read(path)
-        except (ValueError, AssertionError):
-            pass
+    """A file is a OneFileDB (or, failing that, its directory); a directory a FilesystemDB."""
+    if not os.path.isfile(path):
+        return FilesystemDB(path)
+    try:
+        return OneFileDB.read(path)
+    except (ValueError, AssertionError):
         return FilesystemDB(os.path.dirname(path) or '.')
-    return FilesystemDB(path)

@@ -25,49 +25,39 @@ class Wrapper(object):
             spec = toplevels[val['type']]
         self._val, self.spec, self.path, self._params = val, spec, path, params
 
-    # -- dispatch -----------------------------------------------------------
+    # -- dispatch: spec node type -> wrap_<kind> --------------------------------------
+    _KINDS = ((Enum, 'enum'), (Spline, 'spline'), (Scalar, 'scalar'),
+              (RefScalar, 'refscalar'), (dict, 'dict'), (Map, 'Map'), (List, 'List'))
+
     def wrap(self, name, spec, val):
         path = self.path + (name,)
-        if isinstance(spec, Enum):
-            return self.wrap_enum(path, spec, val)
-        if isinstance(spec, Spline):
-            return self.wrap_spline(path, spec, val)
-        if isinstance(spec, Scalar):
-            return self.wrap_scalar(path, spec, val)
-        if isinstance(spec, RefScalar):
-            return self.wrap_refscalar(path, spec, val)
-        if isinstance(spec, dict):
-            return self.wrap_dict(path, spec, val)
-        if isinstance(spec, Map):
-            return self.wrap_Map(path, spec, val)
-        if isinstance(spec, List):
-            return self.wrap_List(path, spec, val)
+        for kind, suffix in self._KINDS:
+            if isinstance(spec, kind):
+                return getattr(self, 'wrap_' + suffix)(path, spec, val)
         return self.wrap_default(path, spec, val)
 
     def wrap_default(self, path, spec, val):
         return val
 
-    def wrap_enum(self, path, spec, val):
-        return val or spec.default
-
     def wrap_spline(self, path, spec, val):
         return val
 
-    def wrap_scalar(self, path, spec, val):
-        return val if val is not None else spec.default
+    def wrap_enum(self, path, spec, val):
+        return val or spec.default
 
-    def wrap_refscalar(self, path, spec, val):
-        return val if val is not None else spec.default
+    def wrap_scalar(self, path, spec, val):
+        return spec.default if val is None else val
+
+    wrap_refscalar = wrap_scalar
 
     def wrap_dict(self, path, spec, val):
         return type(self)(val or {}, spec, path, **self._params)
 
-    def wrap_Map(self, path, spec, val):
-        return self.wrap_dict(path, spec, val)
+    wrap_Map = wrap_dict
 
     def wrap_List(self, path, spec, val):
-        val = val if val is not None else spec.default
-        return [self.wrap(path, spec.type, v) for v in val]
+        items = spec.default if val is None else val
+        return [self.wrap(path, spec.type, v) for v in items]
 
     def get_spec(self, name):
         if isinstance(self.spec, Map):

@@ -25,56 +25,65 @@ _OVERRIDABLE = ('duration', 'fps', 'frame_width', 'start', 'end', 'skip',
                 'shard', 'spp', 'width', 'height')
 
 
+# (group title, [(flags, argparse keywords)]) -- the reference's options
+# (profile.py:17-74), kept as data
+_OPTION_GROUPS = (
+    ('Profile options', [
+        (('-P', '--builtin-profile'), dict(
+            choices=list(BUILTIN.keys()), default='720p',
+            help='Set parameters below from a builtin profile. (default: 720p)')),
+        (('-p', '--profile'), dict(type=argparse.FileType(), metavar='PROFILE',
+                                   help='Set profile from a JSON file.')),
+    ]),
+    ('Temporal options', [
+        (('--duration',), dict(type=float, metavar='TIME',
+                               help='Override base duration in seconds')),
+        (('--fps',), dict(type=float, dest='fps', help='Override frames per second')),
+        (('--start',), dict(metavar='FRAME_NO', type=int,
+                            help='First frame to render (1-indexed, inclusive)')),
+        (('--end',), dict(metavar='FRAME_NO', type=int,
+                          help='Last frame to render (1-indexed, exclusive, negative from end)')),
+        (('--skip',), dict(dest='skip', metavar='N', type=int,
+                           help='Skip N frames between each rendered frame')),
+        (('--shard',), dict(
+            dest='shard', metavar='SECS', type=float,
+            help="Write SECS of output into each file, instead of one frame per file. "
+                 "If set, causes 'start', 'end', and 'skip' to be ignored.")),
+        (('--frame_width',), dict(metavar='SCALE', type=float,
+                                  help='Adjustment factor for temporal frame width.')),
+        (('--still',), dict(action='store_true',
+                            help='Override start, end, and temporal frame width to render '
+                                 'one frame without motion blur.')),
+    ]),
+    ('Spatial options', [
+        (('--spp',), dict(type=int, metavar='SPP', help='Set base samples per pixel')),
+        (('--width',), dict(type=int, metavar='PX')),
+        (('--height',), dict(type=int, metavar='PX')),
+    ]),
+    ('Output options', [
+        (('--codec',), dict(choices=['jpeg', 'png', 'tiff', 'x264', 'vp8', 'vp9', 'prores',
+                                     'raw'])),
+        (('-n',), dict(metavar='NAME', type=str, dest='name',
+                       help='Prefix to use when saving files (default is basename of input)')),
+        (('--suffix',), dict(metavar='NAME', type=str, dest='suffix', default='',
+                             help="Suffix to use when saving files (default '')")),
+        (('-o',), dict(metavar='DIR', type=str, dest='dir', default='.',
+                       help='Output directory')),
+        (('--resume',), dict(action='store_true', dest='resume',
+                             help="Don't overwrite output files that are newer than the input")),
+        (('--subdir',), dict(action='store_true',
+                             help='Use basename as subdirectory of out dir, instead of prefix')),
+    ]),
+)
+
+
 def add_args(parser=None):
-    """Add the profile option groups to ``parser`` (profile.py:17-74)."""
+    """Add the profile option groups to ``parser`` (a new one if None)."""
     parser = argparse.ArgumentParser() if parser is None else parser
-    prof = parser.add_argument_group('Profile options')
-    prof.add_argument('-P', '--builtin-profile', choices=list(BUILTIN.keys()),
-                      default='720p',
-                      help='Set parameters below from a builtin profile. (default: 720p)')
-    prof.add_argument('-p', '--profile', type=argparse.FileType(),
-                      metavar='PROFILE', help='Set profile from a JSON file.')
-
-    tmp = parser.add_argument_group('Temporal options')
-    tmp.add_argument('--duration', type=float, metavar='TIME',
-                     help='Override base duration in seconds')
-    tmp.add_argument('--fps', type=float, dest='fps',
-                     help='Override frames per second')
-    tmp.add_argument('--start', metavar='FRAME_NO', type=int,
-                     help='First frame to render (1-indexed, inclusive)')
-    tmp.add_argument('--end', metavar='FRAME_NO', type=int,
-                     help='Last frame to render (1-indexed, exclusive, negative from end)')
-    tmp.add_argument('--skip', dest='skip', metavar='N', type=int,
-                     help='Skip N frames between each rendered frame')
-    tmp.add_argument('--shard', dest='shard', metavar='SECS', type=float,
-                     help='Write SECS of output into each file, instead of one '
-                          "frame per file. If set, causes 'start', 'end', and "
-                          "'skip' to be ignored.")
-    tmp.add_argument('--frame_width', metavar='SCALE', type=float,
-                     help='Adjustment factor for temporal frame width.')
-    tmp.add_argument('--still', action='store_true',
-                     help='Override start, end, and temporal frame width to '
-                          'render one frame without motion blur.')
-
-    spa = parser.add_argument_group('Spatial options')
-    spa.add_argument('--spp', type=int, metavar='SPP',
-                     help='Set base samples per pixel')
-    spa.add_argument('--width', type=int, metavar='PX')
-    spa.add_argument('--height', type=int, metavar='PX')
-
-    out = parser.add_argument_group('Output options')
-    out.add_argument('--codec', choices=['jpeg', 'png', 'tiff', 'x264', 'vp8',
-                                         'vp9', 'prores', 'raw'])
-    out.add_argument('-n', metavar='NAME', type=str, dest='name',
-                     help='Prefix to use when saving files (default is basename of input)')
-    out.add_argument('--suffix', metavar='NAME', type=str, dest='suffix',
-                     default='', help="Suffix to use when saving files (default '')")
-    out.add_argument('-o', metavar='DIR', type=str, dest='dir', default='.',
-                     help='Output directory')
-    out.add_argument('--resume', action='store_true', dest='resume',
-                     help="Don't overwrite output files that are newer than the input")
-    out.add_argument('--subdir', action='store_true',
-                     help='Use basename as subdirectory of out dir, instead of prefix')
+    for title, options in _OPTION_GROUPS:
+        group = parser.add_argument_group(title)
+        for flags, kw in options:
+            group.add_argument(*flags, **kw)
     return parser
 
 
