@@ -215,6 +215,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--filter-shard', default='band', choices=['band', 'root'],
+                    help='multi-GPU: filter row bands on every GPU (all-reduce + gather) '
+                         'or the whole frame on the root (reduce)')
     ap.add_argument('--workload', default='still1080', choices=sorted(WORKLOADS),
                     help='still1080 = BASELINE configs[1] (default); still4k = configs[2]')
     args = ap.parse_args()
@@ -241,8 +244,11 @@ def main():
     N_, gnm, gprof, tc, rmgr, rdr = frame_setup(n_gpus, rank)
     reducer = None
     if n_gpus > 1:
-        reducer = multigpu.HistReducer(root=0)
+        banded = args.filter_shard == 'band'
+        reducer = multigpu.HistReducer(root=None if banded else 0)
         rmgr.hist_hook = reducer
+        if banded:
+            rmgr.band_filter = multigpu.BandFilter(rank, n_gpus, root=0)
     dim = rmgr.fb.set_dim(gprof.width, gprof.height)
     td = gprof.frame_width(tc) / round(gprof.fps * gprof.duration)
     ts = tc - 0.5 * td
@@ -271,9 +277,9 @@ def main():
         ev_iter1.record(s)
         if reducer is not None:
             reducer(rmgr.fb, dim, s)
-        if reducer is None or rank == 0:
-            for filt in rdr.filts:
-                filt.apply(rmgr.fb, gprof, getattr(gprof.filters, filt.name), dim, tc, s)
+        if rmgr.band_filter is not None or rank == 0:
+            rmgr._filter(rdr, gprof, dim, tc)
+        if rank == 0:
             rdr.out.convert(rmgr.fb, gprof, dim, s)
         ev1.record(s)
 
@@ -389,8 +395,11 @@ def main():
                    'samples_per_step': total, 'frames_per_second': 1e3 / ms_per_step,
                    'l2': 'L2 flushed between timed steps (512 MiB fill)',
                    'timing': 'CUDA events on the launching stream, per step, max over ranks',
-                   'parallelism': 'independent RNG streams per GPU + NCCL reduce'
-                                  if n_gpus > 1 else 'single GPU'},
+                   'parallelism': ('single GPU' if n_gpus == 1 else
+                                   'independent RNG streams per GPU + NCCL all-reduce; filter '
+                                   'chain sharded by row bands, gathered on the root'
+                                   if rmgr.band_filter is not None else
+                                   'independent RNG streams per GPU + NCCL reduce; root filters')},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'iterations/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_my / args.steps},
@@ -401,6 +410,8 @@ def main():
     }
     if reducer is not None:
         line['config']['nccl_reduce_ms'] = reducer.mean_reduce_ms(args.steps)
+        if rmgr.band_filter is not None:
+            line['config']['nccl_gather_ms'] = rmgr.band_filter.mean_gather_ms(args.steps)
     print(json.dumps(line))
 
 

@@ -275,6 +275,19 @@ class DeviceBuffer(object):
         return _CudaArrayView(self, shape, typestr)
 
 
+class DeviceSlice(object):
+    """A window into someone else's allocation (never freed here)."""
+    def __init__(self, buf, offset, nbytes):
+        assert 0 <= offset and offset + nbytes <= buf.nbytes
+        self.ptr, self.nbytes, self._owner = int(buf) + int(offset), int(nbytes), buf
+
+    def __int__(self):
+        return self.ptr
+
+    def view(self, shape, typestr):
+        return _CudaArrayView(self, shape, typestr)
+
+
 class _CudaArrayView(object):
     def __init__(self, buf, shape, typestr):
         self._buf = buf

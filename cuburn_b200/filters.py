@@ -24,6 +24,19 @@ def gauss_coefs(stdev=1):
     return (ctypes.c_float * 7)(*coefs.astype(np.float32))
 
 
+# The first eight of the device's 16 filter directions (code/filters.py:8-17), for
+# working out how far a stencil reaches.
+DIRECTIONS = [(1.0, 0.0), (0.0, 1.0), (1.0, 1.0), (-1.0, 1.0),
+              (1.0, 0.5), (-0.5, 1.0), (1.0, -0.5), (0.5, 1.0)]
+
+
+def reach_rows(pattern, *steps):
+    """Rows a chain of stencils along direction ``pattern`` can reach, each stage
+    ``steps`` taps out (tap offsets are rounded per stage, tex_shear)."""
+    dy = abs(DIRECTIONS[pattern][1])
+    return int(sum(np.ceil(dy * n) for n in steps))
+
+
 def _h(stream):
     return stream.handle if stream is not None else None
 
@@ -36,6 +49,11 @@ class Filter(object):
 
     def apply(self, fb, gprof, params, dim, tc, stream=None):
         raise NotImplementedError()
+
+    def reach(self, gprof, params, tc):
+        """Rows above / below a bin that its result depends on (0: pointwise).  An
+        addition: lets a multi-GPU still filter row bands with exact halos."""
+        return 0
 
     @classmethod
     def register(cls, name):
@@ -72,6 +90,11 @@ class Bilateral(Filter):
                 f32(params.density_pow(tc)), f32(params.gradient(tc)), N.byref(dim), s))
             fb.flip()
 
+    def reach(self, gprof, params, tc):
+        # per direction: taps to radius + 1 (the gradient reads one further), whose
+        # two-octave blur reaches 6 steps, whose density blur reaches 3
+        return sum(reach_rows(p, self.radius + 1, 6, 3) for p in range(self.directions))
+
 
 @Filter.register('logscale')
 class Logscale(Filter):
@@ -94,6 +117,9 @@ class HaloClip(Filter):
         N.check(L.cb_den_blur_1c(fb.d_back.ptr, fb.d_left.ptr, 2, 0, coefs, N.byref(dim), s))
         N.check(L.cb_den_blur_1c(fb.d_left.ptr, fb.d_back.ptr, 3, 0, coefs, N.byref(dim), s))
         N.check(L.cb_haloclip(fb.d_front.ptr, fb.d_left.ptr, gam, N.byref(dim), s))
+
+    def reach(self, gprof, params, tc):
+        return reach_rows(2, 3) + reach_rows(3, 3)
 
 
 def calc_lingam(params, tc):
@@ -119,6 +145,9 @@ class SmearClip(Filter):
         N.check(L.cb_full_blur(fb.d_left.ptr, fb.d_back.ptr, 1, 0, coefs, N.byref(dim), s))
         N.check(L.cb_smearclip(fb.d_front.ptr, fb.d_left.ptr, f32(gam - 1), lin, lingam,
                                N.byref(dim), s))
+
+    def reach(self, gprof, params, tc):
+        return sum(reach_rows(p, 3) for p in (2, 3, 0, 1))
 
 
 @Filter.register('colorclip')

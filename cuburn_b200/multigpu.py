@@ -7,7 +7,11 @@ sharding are available in-process:
 
   * stills: every GPU runs a disjoint share of the frame's samples with its own
     RNG streams into a private float4 histogram; ``HistReducer`` sums them onto
-    the root with one NCCL reduce, and the root runs the filter chain.
+    the root with one NCCL reduce, and the root runs the filter chain.  With
+    ``HistReducer(root=None)`` (all-reduce) + ``BandFilter`` the filter chain is
+    sharded too: every GPU filters a band of rows plus the halo the chain's
+    stencils reach, and the bands are gathered on the root -- bit-identical to
+    filtering the whole frame on one GPU.
   * animations: whole frames are independent (points are re-seeded every frame),
     so ``partition_frames`` deals frames round-robin and no collective is needed.
 
@@ -78,7 +82,8 @@ def make_rank_seeds(rank, world, host_seed, nstreams=262144):
 class HistReducer(object):
     """
     ``RenderManager.hist_hook``: sums the per-GPU float4 histograms onto
-    ``root`` before the filter chain runs there.
+    ``root`` before the filter chain runs there; ``root=None`` leaves the sum on
+    every GPU (all-reduce), which ``BandFilter`` needs.
     """
     def __init__(self, root=0):
         import torch
@@ -102,7 +107,10 @@ class HistReducer(object):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.dist.reduce(t, dst=self.root, op=self.dist.ReduceOp.SUM)
+            if self.root is None:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            else:
+                self.dist.reduce(t, dst=self.root, op=self.dist.ReduceOp.SUM)
             e1.record()
         self._events.append((e0, e1))
 
@@ -110,6 +118,96 @@ class HistReducer(object):
         """Device time of the recorded reduces (call after a synchronize)."""
         evs = self._events[-last:] if last else self._events
         return float(np.mean([a.elapsed_time(b) for a, b in evs])) if evs else None
+
+
+def band_rows(aheight, rank, world):
+    """
+    (row0, row1): the band of accumulation rows `rank` filters.  Bands are equally
+    tall (a multiple of 16 rows, what the filter kernels' grids need) so that one
+    gather moves them; when `aheight` is not a multiple of the band height the last
+    bands slide up and overlap their neighbour -- overlapping rows are computed
+    identically by both owners.
+    """
+    assert aheight % 16 == 0 and aheight > 0
+    band = min(16 * -(-(aheight // 16) // world), aheight)
+    row0 = min(rank * band, aheight - band)
+    return row0, row0 + band
+
+
+def chain_reach(filts, gprof, tc):
+    """Rows of context the filter chain needs around a band, rounded up to 16."""
+    rows = sum(f.reach(gprof, getattr(gprof.filters, f.name, None), tc) for f in filts)
+    return 16 * -(-rows // 16)
+
+
+class BandFilter(object):
+    """
+    ``RenderManager.band_filter``: the filter chain sharded by rows over the GPUs of
+    a still.  Each GPU holds the complete histogram (``HistReducer(root=None)``),
+    runs the unchanged chain on ``FramebufferBand`` = its band plus ``chain_reach``
+    rows either side, and the bands proper are gathered into the root's ``d_front``.
+    Rows inside the halo are wrong near the band's artificial edges and are never
+    used; the band itself is bit-identical to the single-GPU result.
+    """
+    def __init__(self, rank, world, root=0, comm=True):
+        self.rank, self.world, self.root, self.comm = rank, world, root, comm
+        if comm:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+        self._events = []
+
+    def filter_band(self, fb, filts, gprof, dim, tc, stream):
+        """Run the chain on this rank's band + halo; returns (row0, row1)."""
+        from .render import FramebufferBand
+        row0, row1 = band_rows(dim.ah, self.rank, self.world)
+        halo = chain_reach(filts, gprof, tc)
+        band = FramebufferBand(fb, dim, max(row0 - halo, 0), min(row1 + halo, dim.ah))
+        for filt in filts:
+            filt.apply(band, gprof, getattr(gprof.filters, filt.name), band.dim, tc, stream)
+        return row0, row1
+
+    def __call__(self, fb, filts, gprof, dim, tc, stream):
+        row0, row1 = self.filter_band(fb, filts, gprof, dim, tc, stream)
+        if not self.comm or self.world == 1:
+            return
+        torch, dist = self.torch, self.dist
+        full = torch.as_tensor(fb.d_front.view((dim.ah, 4 * dim.astride), '<f4'), device='cuda')
+        ext = torch.cuda.ExternalStream(stream.handle.value)
+        with torch.cuda.stream(ext):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dest = None
+            if self.rank == self.root:
+                dest = [full[slice(*band_rows(dim.ah, r, self.world))]
+                        for r in range(self.world)]
+            dist.gather(full[row0:row1], dest, dst=self.root)
+            e1.record()
+        self._events.append((e0, e1))
+
+    def mean_gather_ms(self, last=None):
+        evs = self._events[-last:] if last else self._events
+        return float(np.mean([a.elapsed_time(b) for a, b in evs])) if evs else None
+
+
+def gather_host_bands(frame, rank, world, root=0):
+    """gloo/CPU twin of BandFilter's gather: `frame` is [aheight, ...]; the root's copy
+    ends up with every rank's band rows."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(frame)
+    row0, row1 = band_rows(frame.shape[0], rank, world)
+    dest = None
+    if rank == root:
+        dest = [torch.empty_like(t[slice(*band_rows(frame.shape[0], r, world))])
+                for r in range(world)]
+    dist.gather(t[row0:row1].contiguous(), dest, dst=root)
+    if rank == root:
+        for r, part in enumerate(dest):
+            a, b = band_rows(frame.shape[0], r, world)
+            t[a:b] = part
+    return t.numpy()
 
 
 def reduce_host_hist(hist, root=0):

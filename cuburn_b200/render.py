@@ -122,6 +122,36 @@ class Framebuffers(object):
         self.d_uleft, self.d_uright = self.d_uright, self.d_uleft
 
 
+class FramebufferBand(object):
+    """
+    Rows [row0, row1) of a ``Framebuffers`` seen as a framebuffer of their own: the
+    same four float4 planes, offset, with ``dim`` narrowed to the band.  Filters run
+    on it unchanged (their stencils clamp at the band's edges exactly as they do at
+    the frame's), and ``flip`` / ``flip_side`` act on the parent, so the parent ends
+    with its planes in the roles the chain left them in.
+    """
+    def __init__(self, fb, dim, row0, row1):
+        assert 0 <= row0 < row1 <= dim.ah and row0 % 16 == 0 and (row1 - row0) % 16 == 0
+        self.fb, self.row0, self.row1 = fb, row0, row1
+        self.dim = N.Dims(dim.w, dim.h, dim.aw, row1 - row0, dim.astride)
+        self._off, self._len = 16 * row0 * dim.astride, 16 * (row1 - row0) * dim.astride
+        self.gutter, self.pool = fb.gutter, fb.pool
+
+    def _plane(self, name):
+        return N.DeviceSlice(getattr(self.fb, name), self._off, self._len)
+
+    d_front = property(lambda self: self._plane('d_front'))
+    d_back = property(lambda self: self._plane('d_back'))
+    d_left = property(lambda self: self._plane('d_left'))
+    d_right = property(lambda self: self._plane('d_right'))
+
+    def flip(self):
+        self.fb.flip()
+
+    def flip_side(self):
+        self.fb.flip_side()
+
+
 class DevSrc(object):
     """Device copies of the genome's interpolation sources (render.py:172-190)."""
     max_knots = packer_mod.MAX_KNOTS
@@ -375,6 +405,19 @@ class RenderManager(object):
                                               N.byref(dim), s.handle))
         self.last_iter_samples = n
 
+    # -- filter ----------------------------------------------------------------------
+    # multi-GPU stills: a multigpu.BandFilter makes every GPU filter a band of rows
+    # (with halos) of the combined histogram and gathers the bands on the root
+    band_filter = None
+
+    def _filter(self, rdr, gprof, dim, tc):
+        if self.band_filter is not None:
+            self.band_filter(self.fb, rdr.filts, gprof, dim, tc, self.stream_a)
+            return
+        for filt in rdr.filts:
+            params = getattr(gprof.filters, filt.name)
+            filt.apply(self.fb, gprof, params, dim, tc, self.stream_a)
+
     # -- frame -----------------------------------------------------------------------
     def queue_frame(self, rdr, gnm, gprof, tc, copy=True, frame_seed=None):
         """
@@ -414,9 +457,7 @@ class RenderManager(object):
             self.hist_hook(self.fb, dim, self.stream_a)
         if self.copy_evt:
             self.stream_a.wait_for_event(self.copy_evt)
-        for filt in rdr.filts:
-            params = getattr(gprof.filters, filt.name)
-            filt.apply(self.fb, gprof, params, dim, tc, self.stream_a)
+        self._filter(rdr, gprof, dim, tc)
         rdr.out.convert(self.fb, gprof, dim, self.stream_a)
         self.filt_evt = N.Event().record(self.stream_a)
         h_out = rdr.out.copy(self.fb, dim, self.fb.pool, self.stream_a)

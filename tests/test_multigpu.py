@@ -101,6 +101,140 @@ def test_gloo_hist_reduce_world2(built, tmp_path):
     assert 0.9 * total < inside <= total
 
 
+def test_band_rows_cover_the_grid_with_equal_bands():
+    from cuburn_b200 import multigpu
+    for ah in (16, 208, 384, 752, 1104, 2192, 4352):
+        for world in (1, 2, 3, 4, 8):
+            bands = [multigpu.band_rows(ah, r, world) for r in range(world)]
+            assert len({b - a for a, b in bands}) == 1            # one gather moves them
+            assert all(a % 16 == 0 and (b - a) % 16 == 0 and 0 <= a < b <= ah for a, b in bands)
+            covered = np.zeros(ah, bool)
+            for a, b in bands:
+                covered[a:b] = True
+            assert covered.all()
+            assert bands[0][0] == 0 and bands[-1][1] == ah
+
+
+def _chain_and_profile():
+    from cuburn_b200 import samples, profile, filters
+    gnm = samples.g3()
+    gprof = profile.wrap(dict(width=1920, height=1080, spp=100, frame_width=0, start=1, end=2), gnm)
+    tc = profile.enumerate_times(gprof)[0][1][0]
+    return filters.create(gprof), gprof, tc
+
+
+def _random_hist(ah, astride, seed=5):
+    rs = np.random.RandomState(seed)
+    dens = rs.gamma(0.3, 40.0, size=(ah, astride)).astype(np.float32)
+    dens[rs.rand(ah, astride) < 0.3] = 0
+    col = rs.rand(ah, astride, 3).astype(np.float32)
+    hist = np.empty((ah, astride, 4), np.float32)
+    hist[..., 0] = dens * col[..., 0]
+    hist[..., 1] = dens * (col[..., 1] * 0.6 + 0.2)
+    hist[..., 2] = dens * (col[..., 2] * 0.6 + 0.2)
+    hist[..., 3] = dens
+    return hist
+
+
+def _oracle_band(hist, rank, world, halo):
+    from cuburn_b200 import multigpu
+    from oracle import filters_ref as F
+    ah = hist.shape[0]
+    a, b = multigpu.band_rows(ah, rank, world)
+    e0, e1 = max(a - halo, 0), min(b + halo, ah)
+    out = F.default_chain(hist[e0:e1], 1920, 1080, 0.5, 100)
+    return a, b, out[a - e0:b - e0]
+
+
+def test_chain_reach_is_enough_halo_for_the_oracle_chain():
+    """Filtering a band plus `chain_reach` rows of halo with the CPU restatement of
+    the default chain gives exactly the rows full-frame filtering gives; a 16-row halo
+    does not (so the test can see a missing halo)."""
+    from cuburn_b200 import multigpu
+    from oracle import filters_ref as F
+    filts, gprof, tc = _chain_and_profile()
+    halo = multigpu.chain_reach(filts, gprof, tc)
+    assert halo == 160
+    hist = _random_hist(544, 64)
+    full = F.default_chain(hist, 1920, 1080, 0.5, 100)
+    for rank in range(3):
+        a, b, band = _oracle_band(hist, rank, 3, halo)
+        assert np.array_equal(band.view(np.uint32), full[a:b].view(np.uint32)), rank
+    a, b, band = _oracle_band(hist, 1, 3, 16)
+    assert not np.array_equal(band.view(np.uint32), full[a:b].view(np.uint32))
+
+
+def _band_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from cuburn_b200 import multigpu
+    multigpu.init_process_group('gloo')
+    filts, gprof, tc = _chain_and_profile()
+    hist = _random_hist(400, 64)
+    a, b, band = _oracle_band(hist, rank, world, multigpu.chain_reach(filts, gprof, tc))
+    frame = np.full_like(hist, np.nan)
+    frame[a:b] = band
+    frame = multigpu.gather_host_bands(frame, rank, world, root=0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, 'banded.npy'), frame)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_banded_filter_world2(built, tmp_path):
+    """Two ranks filter one band each (oracle chain) and gather on the root: the
+    assembled frame equals the frame filtered whole."""
+    import torch.multiprocessing as mp
+    from oracle import filters_ref as F
+    mp.spawn(_band_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    full = F.default_chain(_random_hist(400, 64), 1920, 1080, 0.5, 100)
+    banded = np.load(tmp_path / 'banded.npy')
+    assert np.array_equal(banded.view(np.uint32), full.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_banded_filter_chain_is_bit_identical(native, built):
+    """Every band of the sharded filter chain (BandFilter.filter_band on one GPU,
+    playing each rank in turn) equals the same rows of the frame filtered whole."""
+    N = native
+    from cuburn_b200 import samples, render, profile, multigpu
+    gnm = samples.g6f()
+    gprof = profile.wrap(dict(width=256, height=1000, spp=60, frame_width=0, start=1, end=2), gnm)
+    tc = profile.enumerate_times(gprof)[0][1][0]
+    rmgr = render.RenderManager(seed=4)
+    rdr = render.Renderer(gnm, gprof)
+    dim = rmgr.fb.set_dim(256, 1000)
+    rmgr._copy(rdr, gnm)
+    rmgr._interp(rdr, gnm, dim, tc, 0.0)
+    rmgr._iter(rdr, gnm, gprof, dim, tc)
+    s = rmgr.stream_a
+    s.synchronize()
+    shape = (dim.ah, dim.astride, 4)
+    hist = N.from_device(rmgr.fb.d_front, shape, np.float32)
+    assert hist[..., 3].sum() > 0.5 * 256 * 1000 * 60
+    rmgr._filter(rdr, gprof, dim, tc)
+    s.synchronize()
+    full = N.from_device(rmgr.fb.d_front, shape, np.float32)
+    assert np.isfinite(full).all() and full[..., 3].max() > 0
+    world = 4
+    halo = multigpu.chain_reach(rdr.filts, gprof, tc)
+    assert dim.ah > multigpu.band_rows(dim.ah, 0, world)[1] + 2 * halo     # a real interior band
+    for rank in range(world):
+        N.memcpy_htod(rmgr.fb.d_front, hist, s)
+        for plane in (rmgr.fb.d_back, rmgr.fb.d_left, rmgr.fb.d_right):
+            N.fill32(plane, 4 * dim.ah * dim.astride, np.float32(np.nan), s)
+        rmgr.band_filter = multigpu.BandFilter(rank, world, comm=False)
+        rmgr._filter(rdr, gprof, dim, tc)
+        s.synchronize()
+        a, b = multigpu.band_rows(dim.ah, rank, world)
+        band = N.from_device(rmgr.fb.d_front, shape, np.float32)[a:b]
+        assert np.array_equal(band.view(np.uint32), full[a:b].view(np.uint32)), rank
+    rmgr.band_filter = None
+
+
 @pytest.mark.gpu
 def test_hist_view_is_zero_copy(native, built):
     """torch sees the library's device buffer through __cuda_array_interface__."""

@@ -24,9 +24,9 @@ for gname, w, h, spp in cases:
         names, hdrs = itergen.load_headers()
         mod = N.Module(src, 'iter.cu', hdrs, names, itergen.NVRTC_OPTIONS)
         rdr = render.Renderer(gnm, gprof)
-        rdr.mod, rdr._mod_const = mod, mod
+        rdr._variants[(still, False)] = mod
         if not still:
-            gprof2 = profile.wrap(dict(width=w, height=h, spp=spp, frame_width=1e-9, start=1, end=2), gnm)
+            gprof2 = profile.wrap(dict(width=w, height=h, spp=spp, frame_width=float(os.environ.get('FW', 1e-9)), start=1, end=2), gnm)
         else:
             gprof2 = gprof
         rmgr._copy(rdr, gnm)
