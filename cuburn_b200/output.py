@@ -8,11 +8,16 @@ Mirrors the reference interface (cuburn/output.py:28-66, 411-434):
 pinned memory and returns the array; ``.encode(host_frame | None)`` returns
 ``({suffix: file-like}, [(key, log)])``.  JPEG / PNG go through Pillow; 16-bit
 TIFF is written by a small built-in baseline-TIFF writer; the planar YUV
-formats are available as raw planes (``type: raw``) for an external encoder --
-the x264 / vpx / ffmpeg subprocess plumbing of the reference is out of scope.
+formats are available as raw planes (``type: raw``); the video types stream
+frames into an external encoder process (``x264``, ``vpxenc``, ``ffmpeg``) with
+the reference's command lines (output.py:139-409) -- the binaries are not part of
+this package, and a missing one is reported when the first frame is encoded.
 """
 import io
+import shlex
 import struct
+import subprocess
+import tempfile
 
 import numpy as np
 
@@ -165,6 +170,218 @@ class RawPlanarOutput(Output):
         return {'.' + self.pix_fmt: io.BytesIO(np.ascontiguousarray(buf).tobytes())}, []
 
 
+class EncoderPipe(object):
+    """
+    One external encoder process: raw frames go to its stdin, its stdout is
+    collected in an unnamed temporary file (or it writes a named file itself), its
+    stderr becomes the log.  ``finish()`` closes stdin, waits, and returns
+    ``(file positioned at 0, log)``; a non-zero exit status is an ``IOError``, as
+    in the reference (output.py:172-173, 255-256).
+    """
+    def __init__(self, argv, name, named_suffix=None):
+        self.name = name
+        self.named = None
+        if named_suffix is not None:
+            # the encoder wants a seekable path (mov muxer): it writes the file itself
+            self.named = tempfile.NamedTemporaryFile(suffix=named_suffix)
+            argv = [a.replace('{fn}', self.named.name) for a in argv]
+            self.outf = None
+        else:
+            self.outf = tempfile.TemporaryFile()
+        try:
+            self.proc = subprocess.Popen([str(a) for a in argv], stdin=subprocess.PIPE,
+                                         stderr=subprocess.PIPE,
+                                         stdout=self.outf if self.outf is not None
+                                         else subprocess.DEVNULL)
+        except OSError as e:
+            raise IOError('cannot start %s encoder "%s": %s' % (name, argv[0], e))
+        self._log = []
+
+    def write(self, buf):
+        try:
+            self.proc.stdin.write(memoryview(np.ascontiguousarray(buf)).cast('B'))
+        except (IOError, OSError) as e:
+            raise IOError('%s stopped reading frames: %s\n%s'
+                          % (self.name, e, self.proc.stderr.read().decode(errors='replace')))
+
+    def finish(self):
+        _, log = self.proc.communicate()
+        if self.proc.returncode:
+            raise IOError('%s exited with an error\n%s'
+                          % (self.name, log.decode(errors='replace')))
+        if self.named is not None:
+            outf = open(self.named.name, 'rb')      # a new handle; the name goes away
+            self.named.close()
+        else:
+            outf = self.outf
+            outf.seek(0)
+        return outf, log.decode(errors='replace')
+
+
+class X264Output(Output):
+    """16-bit RGB frames into ``x264`` (output.py:196-311); with ``alpha`` a second
+    encoder receives the alpha plane as the luma of a 4:2:0 stream with flat chroma."""
+    fmt = N.FMT_RGBA_U16
+    dtype = 'u2'
+    profiles = {'normal': '--profile high444 --level 4.2', '': ''}
+    base = ('--no-progress --input-depth 16 --sync-lookahead 0 '
+            '--rc-lookahead 5 --muxer raw -o - - --log-level debug')
+
+    def __init__(self, profile='normal', csp='i444', crf=15, command='x264', x264opts='',
+                 alpha=False):
+        self.args = shlex.split(' '.join([command, self.base, self.profiles[profile],
+                                          '--crf', str(crf), x264opts]))
+        self.alpha, self.csp = alpha, csp
+        self.framesize = None
+        self.color = self.matte = None
+
+    def shape(self, dim):
+        return (dim.h, dim.w, 4)
+
+    def _spawn(self, framesize, matte):
+        extras = ['--input-csp', 'yv12' if matte else 'rgb', '--demuxer', 'raw',
+                  '--input-res', '%dx%d' % (framesize[1], framesize[0])]
+        if matte:
+            extras += ['--output-csp', 'i420', '--chroma-qp-offset', '24']
+        else:
+            extras += ['--output-csp', self.csp]
+        return EncoderPipe(self.args + extras, 'x264')
+
+    def _flush(self):
+        if self.color is None:
+            return {}, []
+        outf, log = self.color.finish()
+        self.color = None
+        if self.matte is not None:
+            aoutf, alog = self.matte.finish()
+            self.matte = None
+            return ({'_color.h264': outf, '_alpha.h264': aoutf},
+                    [('x264_color', log), ('x264_alpha', alog)])
+        return {'.h264': outf}, [('x264_color', log)]
+
+    def encode(self, buf):
+        out = ({}, [])
+        if buf is None or self.framesize != buf.shape[:2]:
+            out = self._flush()          # a new frame size starts a new stream
+        if buf is None:
+            return out
+        if self.color is None:
+            self.framesize = buf.shape[:2]
+            self.color = self._spawn(self.framesize, False)
+            if self.alpha:
+                self.matte = self._spawn(self.framesize, True)
+        self.color.write(buf[:, :, :3])
+        if self.matte is not None:
+            self.matte.write(buf[:, :, 3])
+            self.matte.write(np.full(buf.shape[0] * buf.shape[1] // 2, 32767, 'u2'))
+        return out
+
+
+class VPxOutput(Output):
+    """Planar YUV frames into ``vpxenc`` (output.py:313-409)."""
+    base = ('--end-usage=3 -p 1 -q --cpu-used=-8 --lag-in-frames=5 '
+            '--min-q=2 --disable-kf --arnr-maxframes=3 -o - -')
+    _PIX = {  # pix_fmt: (device format, dtype, extra encoder flags)
+        'yuv420p': (N.FMT_YUV444P, 'u1', []),       # subsampled on the host, see encode
+        'yuv444p': (N.FMT_YUV444P, 'u1', ['--profile=1', '--i444']),
+        'yuv420p10': (N.FMT_YUV420P10, 'u2', ['-b', '10', '--input-bit-depth=10', '--profile=2']),
+        'yuv444p10': (N.FMT_YUV444P10, 'u2', ['-b', '10', '--input-bit-depth=10', '--profile=3',
+                                              '--i444']),
+        'yuv444p12': (N.FMT_YUV444P12, 'u2', ['-b', '12', '--input-bit-depth=12', '--profile=3',
+                                              '--i444']),
+    }
+
+    def __init__(self, codec='vp9', fps=24, crf=15, pix_fmt='yuv420p', command='vpxenc'):
+        if pix_fmt not in self._PIX:
+            raise ValueError('Invalid pix_fmt: ' + pix_fmt)
+        if pix_fmt != 'yuv420p' and codec != 'vp9':
+            raise ValueError('%s needs codec vp9' % pix_fmt)
+        self.codec, self.pix_fmt = codec, pix_fmt
+        self.fmt, self.dtype, extra = self._PIX[pix_fmt]
+        self.args = shlex.split(command) + self.base.split() + extra
+        self.args += ['--codec=' + codec, '--cq-level=' + str(crf), '--fps=%d/1' % fps]
+        if codec == 'vp9':
+            self.args += ['-t', '4']
+        self.dim = None
+        self.pipe = None
+
+    def shape(self, dim):
+        if self.pix_fmt == 'yuv420p10':
+            return (dim.h * dim.w * 6 // 4,)
+        return (3, dim.h, dim.w)
+
+    def convert(self, fb, gnm, dim, stream=None):
+        self.dim = dim
+        launchC(self.fmt, dim, fb, stream)
+
+    def _spawn(self, w, h):
+        extras = ['-w', w, '-h', h]
+        columns = int(max(0, min(3, np.log2(w) - 8.9)))
+        if columns:
+            extras.append('--tile-columns=%d' % columns)
+        return EncoderPipe(self.args + extras, 'vpxenc')
+
+    def encode(self, buf):
+        if buf is None:
+            if self.pipe is None:
+                return {}, []
+            outf, log = self.pipe.finish()
+            self.pipe = None
+            return {'.webm': outf}, [('webm', log)]
+        if self.pipe is None:
+            if self.dim is not None:
+                width, height = self.dim.w, self.dim.h
+            elif buf.ndim == 3:
+                height, width = buf.shape[1:]
+            else:
+                raise ValueError('frame size unknown: convert() has not run')
+            self.pipe = self._spawn(width, height)
+        if self.pix_fmt == 'yuv420p':
+            # 4:4:4 planes from the device, chroma decimated here (output.py:394-398)
+            self.pipe.write(buf[0])
+            self.pipe.write(buf[1, ::2, ::2])
+            self.pipe.write(buf[2, ::2, ::2])
+        else:
+            self.pipe.write(buf)
+        return {}, []
+
+
+class ProResOutput(Output):
+    """12-bit 4:4:4 planes into ``ffmpeg -c:v prores`` (output.py:139-194); the mov
+    muxer needs a seekable file, so ffmpeg writes a named temporary file."""
+    fmt = N.FMT_YUV444P12
+    dtype = 'u2'
+    cmd = ('-loglevel panic -f rawvideo -pix_fmt yuv444p12le -s {w}x{h} -r {fps} -i - '
+           '-c:v prores -f mov -y {fn}')
+
+    def __init__(self, fps=24, command='ffmpeg'):
+        self.fps, self.command = fps, command
+        self.dim = None
+        self.pipe = None
+
+    def shape(self, dim):
+        return (3, dim.h, dim.w)
+
+    def convert(self, fb, gnm, dim, stream=None):
+        self.dim = dim
+        launchC(self.fmt, dim, fb, stream)
+
+    def encode(self, buf):
+        if buf is None:
+            if self.pipe is None:
+                return {}, []
+            outf, _ = self.pipe.finish()
+            self.pipe = None
+            return {'.mov': outf}, []
+        if self.pipe is None:
+            h, w = (self.dim.h, self.dim.w) if self.dim is not None else buf.shape[1:]
+            argv = shlex.split(self.command) + \
+                [a.format(w=w, h=h, fps=self.fps, fn='{fn}') for a in self.cmd.split()]
+            self.pipe = EncoderPipe(argv, 'ffmpeg', named_suffix='.mov')
+        self.pipe.write(buf)
+        return {}, []
+
+
 _EXT = dict(jpeg='.jpg', png='.png', tiff='.tiff', x264='.h264', prores='.mov',
             vp8='.webm', vp9='.webm', raw='.raw')
 
@@ -189,9 +406,10 @@ def get_output_for_profile(gprof):
         return TiffOutput(**opts)
     if handler == 'raw':
         return RawPlanarOutput(**opts)
-    if handler in ('x264', 'vp8', 'vp9', 'prores'):
-        raise NotImplementedError(
-            'output type "%s" pipes frames to an external encoder binary, which '
-            'this build does not drive; use type "raw" with the matching pix_fmt '
-            'and feed the planes to the encoder yourself' % handler)
+    if handler == 'x264':
+        return X264Output(**opts)
+    if handler in ('vp8', 'vp9'):
+        return VPxOutput(codec=handler, fps=gprof.fps, **opts)
+    if handler == 'prores':
+        return ProResOutput(fps=gprof.fps, **opts)
     raise ValueError('Invalid output type "%s".' % handler)

@@ -208,6 +208,36 @@ def test_main_cli_renders_flam3_file(native, built, tmp_path):
     assert r2.returncode == 0 and 'spark_00002' not in r2.stderr
 
 
+def test_video_outputs_stream_rendered_frames(native, built, tmp_path):
+    """Frames rendered through queue_frame reach the x264 / vpxenc pipes in the pixel
+    format each encoder expects (a stand-in script plays the encoder)."""
+    import stat
+    from test_encoders import FAKE
+    from cuburn_b200 import samples, render, profile
+    fake = tmp_path / 'fakeenc'
+    fake.write_text(FAKE)
+    fake.chmod(fake.stat().st_mode | stat.S_IXUSR)
+    gnm = samples.g6f(animated=True)
+    for otype, suffix, frame_bytes in (
+            (dict(type='x264', command=str(fake)), '.h264', 320 * 180 * 3 * 2),
+            (dict(type='vp9', command=str(fake), pix_fmt='yuv420p10'), '.webm', 320 * 180 * 3),
+            (dict(type='vp8', command=str(fake)), '.webm', 320 * 180 * 3 // 2),
+            (dict(type='prores', command=str(fake)), '.mov', 320 * 180 * 3 * 2)):
+        gprof = profile.wrap(dict(width=320, height=180, spp=40, fps=24, duration=1.0,
+                                  output=otype), gnm)
+        times = [t[0] for _, t in profile.enumerate_times(gprof)][:3]
+        rmgr = render.RenderManager(seed=2)
+        rdr = render.Renderer(gnm, gprof)
+        for t in times:
+            evt, buf = rmgr.queue_frame(rdr, gnm, gprof, t)
+            evt.synchronize()
+            assert rdr.out.encode(buf) == ({}, [])
+        media, logs = rdr.out.encode(None)
+        data = media[suffix].read()
+        assert len(data) == 3 * frame_bytes, otype
+        assert np.frombuffer(data, 'u1').std() > 1       # an image, not a constant
+
+
 def test_frame_seed_makes_frames_order_independent(native, built):
     """T11 (animation): with per-frame seeds a frame does not depend on what was rendered
     before it, so frames dealt round-robin to different GPUs equal a sequential render
