@@ -182,17 +182,23 @@ int cb_memcpy_d2d(cb_dptr dst, cb_dptr src, size_t bytes, cb_stream s) {
 }  // extern "C"
 
 // ---- fill ---------------------------------------------------------------------
-// Vectorised grid-stride fill: uint4 stores for the aligned body, scalar tail.
+// Each thread issues FILL_PER independent 16-byte stores per trip (a CTA covers
+// FILL_PER contiguous 4 KiB runs), scalar tail for the last nwords % 4.
+#define FILL_PER 8
 __global__ void __launch_bounds__(256)
 k_fill32(uint32_t *dst, size_t nwords, uint32_t value) {
-    size_t nvec = nwords >> 2;
-    uint4 v = make_uint4(value, value, value, value);
+    const size_t nvec = nwords >> 2;
+    const uint4 v = make_uint4(value, value, value, value);
     uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride)
-        d4[i] = v;
-    size_t tail = nvec << 2;
-    size_t t = tail + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t chunk = (size_t)256 * FILL_PER;
+    for (size_t base = (size_t)blockIdx.x * chunk; base < nvec; base += (size_t)gridDim.x * chunk) {
+#pragma unroll
+        for (int k = 0; k < FILL_PER; k++) {
+            size_t i = base + (size_t)k * 256 + threadIdx.x;
+            if (i < nvec) d4[i] = v;
+        }
+    }
+    size_t t = (nvec << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nwords) dst[t] = value;
 }
 
@@ -200,8 +206,9 @@ extern "C" int cb_fill32(cb_dptr dst, size_t nwords, uint32_t value, cb_stream s
     if (nwords == 0) return CB_OK;
     CB_REQUIRE((dst & 15) == 0, "fill destination must be 16-byte aligned");
     size_t nvec = nwords >> 2;
-    size_t want = (nvec + 255) / 256;
-    int grid = (int)(want < 1 ? 1 : (want > (size_t)cb_sm_count() * 8 ? (size_t)cb_sm_count() * 8 : want));
+    size_t want = (nvec + 256 * FILL_PER - 1) / (256 * FILL_PER);
+    size_t cap = (size_t)cb_sm_count() * 8;
+    int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     k_fill32<<<grid, 256, 0, cb_cs(s)>>>(cb_ptr<uint32_t>(dst), nwords, value);
     CB_LAUNCH_CHECK();
     return CB_OK;

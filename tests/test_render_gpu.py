@@ -44,6 +44,59 @@ def test_frame_psnr_vs_oracle(native, built, gname, spp):
     assert val >= 40.0, val
 
 
+def test_full_size_1080p_still_properties(native, built):
+    """BASELINE config 2 at its real size (1920x1080, 2000 spp, G6F), where the oracle
+    is too slow to run: properties that do not depend on the size.
+      * conservation: the density plane sums to an integer, every launched sample is
+        either in the grid or was rejected by the bounds test (a few per cent);
+      * every bin count is a whole number and colour sums stay inside the palette's
+        range per sample;
+      * the swizzled accumulation layout is a permutation: linear and swizzled
+        renders of the same seeds agree in their totals and statistically per block;
+      * two renders with independent RNG streams agree to >= 40 dB as 8-bit frames."""
+    N = native
+    from cuburn_b200 import samples, render
+    gnm = samples.g6f()
+    w, h, spp = 1920, 1080, 2000
+    gprof, tc = still_profile(gnm, w, h, spp)
+    rmgr = render.RenderManager(seed=5)
+    rdr = render.Renderer(gnm, gprof)
+    dim = rmgr.fb.set_dim(w, h)
+    shape = (dim.ah, dim.astride, 4)
+    rmgr._copy(rdr, gnm)
+    rmgr._interp(rdr, gnm, dim, tc, 0.0)
+    hists = {}
+    for layout in (True, False):
+        rmgr.fb.reseed(5)
+        rmgr.swizzle = layout
+        rmgr._iter(rdr, gnm, gprof, dim, tc)
+        rmgr.stream_a.synchronize()
+        hists[layout] = N.from_device(rmgr.fb.d_front, shape, np.float32).astype(np.float64)
+    rmgr.swizzle = 'auto'
+    n = w * h * spp
+    for hist in hists.values():
+        count = hist[..., 3]
+        total = count.sum()
+        assert total == np.floor(total) and 0.90 * n <= total <= n
+        assert np.array_equal(count, np.floor(count))
+        live = count > 0
+        for ch in range(3):           # (Y, U + 0.5, V + 0.5) of 8-bit colours, / 255
+            mean = hist[..., ch][live] / count[live]
+            assert mean.min() >= -1e-6 and mean.max() <= 1.0 + 1e-6
+    a, b = hists[True], hists[False]
+    assert abs(a[..., 3].sum() - b[..., 3].sum()) <= 2e-4 * n
+    blk = lambda x: x[:1104, :1920, 3].reshape(69, 16, 60, 32).sum((1, 3))
+    assert np.abs(blk(a) - blk(b)).sum() / blk(a).sum() < 0.01
+    frames = []
+    for seed in (101, 202):
+        evt, frame = rmgr.queue_frame(rdr, gnm, gprof, tc, frame_seed=seed)
+        evt.synchronize()
+        frames.append(np.array(frame))
+    assert frames[0].shape == (h, w, 4) and frames[0][..., :3].max() > 200
+    assert not np.array_equal(frames[0], frames[1])
+    assert psnr(frames[0][..., :3], frames[1][..., :3]) >= 40.0
+
+
 def test_queue_frame_pipelining_and_encode(native, built):
     from cuburn_b200 import samples, render
     from PIL import Image
