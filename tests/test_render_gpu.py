@@ -97,6 +97,52 @@ def test_full_size_1080p_still_properties(native, built):
     assert psnr(frames[0][..., :3], frames[1][..., :3]) >= 40.0
 
 
+@pytest.mark.parametrize('gname,w,h,spp,modes', [
+    ('G6F', 3840, 2160, 4000, ('float4',)),                  # BASELINE config 3
+    ('G24H', 7680, 4320, 2000, ('packed', 'float4'))])       # BASELINE config 5
+def test_full_size_4k_8k_conservation(native, built, gname, w, h, spp, modes):
+    """BASELINE configs 3 and 5 at their real sizes: every sample is accounted for
+    (whole-number density, sum within the bounds-test losses of the launched count),
+    colour sums stay in range, and at 8K the packed-u64 accumulation (what 'auto'
+    picks there) and the float4 one agree in their totals and per 64x64 block."""
+    N = native
+    from cuburn_b200 import samples, render
+    gnm = samples.GENOMES[gname]()
+    gprof, tc = still_profile(gnm, w, h, spp)
+    rmgr = render.RenderManager(seed=6)
+    rdr = render.Renderer(gnm, gprof)
+    dim = rmgr.fb.set_dim(w, h)
+    nbins = dim.ah * dim.astride
+    assert rmgr._use_packed(nbins) == (modes[0] == 'packed')         # what 'auto' would do
+    rmgr._copy(rdr, gnm)
+    rmgr._interp(rdr, gnm, dim, tc, 0.0)
+    n = w * h * spp
+    blocks = {}
+    for mode in modes:
+        rmgr.accumulate = mode
+        rmgr._iter(rdr, gnm, gprof, dim, tc)
+        rmgr.stream_a.synchronize()
+        assert rmgr.last_iter_samples == n
+        hist = N.from_device(rmgr.fb.d_front, (dim.ah, dim.astride, 4), np.float32)
+        count = hist[..., 3].astype(np.float64)
+        total = count.sum()
+        assert total == np.floor(total) and 0.85 * n <= total <= n, (total, n)
+        assert np.array_equal(count, np.floor(count))
+        live = count > 0
+        for ch in range(3):
+            mean = hist[..., ch][live] / count[live]
+            assert mean.min() >= -1e-4 and mean.max() <= 1.0 + 1e-4
+        hh, ww = dim.ah // 64 * 64, dim.astride // 64 * 64
+        blocks[mode] = count[:hh, :ww].reshape(hh // 64, 64, ww // 64, 64).sum((1, 3))
+        del hist, count
+    rmgr.accumulate = 'auto'
+    if len(modes) == 2:
+        a, b = blocks[modes[0]], blocks[modes[1]]
+        assert abs(a.sum() - b.sum()) <= 2e-4 * n
+        assert np.abs(a - b).sum() / a.sum() < 0.01
+    rmgr.fb.free()
+
+
 def test_queue_frame_pipelining_and_encode(native, built):
     from cuburn_b200 import samples, render
     from PIL import Image
