@@ -10,6 +10,9 @@
 // loads through L1/L2 are the natural replacement: neighbours are addressed
 // with clamp-to-edge indices.  This file is compiled with
 // --use_fast_math like the reference's modules (code/util.py:96).
+#include <math.h>
+#include <string.h>
+
 #include "cb_common.h"
 
 #define K_SQRT2 1.41421353816986f
@@ -516,6 +519,368 @@ k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern
                                            gspeed, lspa, offs, loffs, dim);
 }
 
+// ---- sliding-window bilateral pass for the y-major directions ---------------------
+// k_bilateral_fast is bound by L1 wavefronts: every pixel loads 2 x 31 records that its
+// neighbours along the direction load as well.  For directions whose taps advance one
+// row per step, a thread here owns BW_P pixels spaced BW_S steps apart along the
+// direction (lanes run along x, so every load stays coalesced) and walks ONE window of
+// 33 + BW_S * (BW_P - 1) records that serves all of them: 9 (S = 1) or 11.25 (S = 4)
+// record loads per pixel instead of 33, and everything that depends on the record only
+// (its reciprocal density, the two Gompertz exponentials of its gradient) is computed
+// once per record instead of once per (pixel, tap) pair.
+//   S = 1: directions (0,1), (1,1), (-1,1) -- tap s of the window is s * dir exactly.
+//   S = 4: directions (-.5,1), (.5,1) -- tex_shear rounds half-steps to even, which is
+//          invariant under shifts by 4 steps (= 2 whole columns), so pixels 4 steps
+//          apart see the same window: shear(4j + r) = shear(4j) + shear(r).
+// A block covers 32 rows x 32 columns, sheared: the pixel j of a thread sits at column
+// x + off(S j).x (mod astride).  Blocks whose window leaves the grid, and rows beyond
+// aheight, take the per-pixel clamped path with identical arithmetic.
+#define BW_P 4
+#define BW_MAXREC (33 + 4 * (BW_P - 1))
+struct bilat_tab {
+    float lspa[16];             // log2 of the spatial kernel at |r|
+    int loff[BW_MAXREC];        // linear offset of window record k (s = k - 16)
+    short2 off[BW_MAXREC];      // (dx, dy) of window record k
+    int xlo, xhi, ylo, yhi;     // extent of the window offsets
+};
+
+struct bilat_consts { float cscale2, dscale, gspeed; };
+
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two lanes of arithmetic per issue
+// slot.  The window kernel is issue-bound, so the two pixels of a pair share every
+// instruction of the colour distance and of the accumulation.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// What a record contributes, broadcast into both lanes.
+struct bilat_rec {
+    f32x2 x, y, z, w, pdrcp;    // the pixel (raw sums) and 1 / density
+    float pow, gplus, gminus;   // density^dpow, Gompertz terms for taps after / before
+    bool live;
+};
+// Two pixels' running state.
+struct bilat_duo {
+    f32x2 ncx, ncy, ncz;        // minus the centres' normalised colours
+    float cpow0, cpow1;
+    bool live0, live1;
+    f32x2 ax, ay, az, aw, ws;
+};
+
+// log2 weight of one (record, pixel) pair but for the colour term; R = tap index of the
+// record relative to the pixel.
+template <int R>
+__device__ __forceinline__ float bilat_weight(float cdiff, bool both_live, float cpow,
+                                              const bilat_rec &rec, const bilat_tab &tab,
+                                              const bilat_consts &kc) {
+    if (R < -15 || R > 15) return 0.0f;          // not a tap of this pixel
+    if (!both_live) cdiff = 0.5f;
+    float e = kc.dscale * fabsf(cpow - rec.pow) + tab.lspa[R < 0 ? -R : R];
+    e += kc.cscale2 * cdiff;
+    if (R > 0) e -= rec.gplus;
+    if (R < 0) e -= rec.gminus;
+    return exp2f(e);
+}
+
+template <int S, int K, int D>
+struct bilat_duos {
+    // pixel pairs D .. BW_P/2-1 against window record K (s = K - 16)
+    static __device__ __forceinline__ void run(const bilat_rec &rec, bilat_duo *duo,
+                                               const bilat_tab &tab, const bilat_consts &kc) {
+        constexpr int R0 = K - 16 - S * (2 * D), R1 = K - 16 - S * (2 * D + 1);
+        constexpr bool in0 = R0 >= -15 && R0 <= 15, in1 = R1 >= -15 && R1 <= 15;
+        if (in0 || in1) {
+            bilat_duo &d = duo[D];
+            f32x2 yd = fma2(rec.x, rec.pdrcp, d.ncx);
+            f32x2 ud = fma2(rec.y, rec.pdrcp, d.ncy);
+            f32x2 vd = fma2(rec.z, rec.pdrcp, d.ncz);
+            f32x2 cd = fma2(vd, vd, fma2(ud, ud, mul2(yd, yd)));
+            float c0, c1;
+            unpk2(cd, c0, c1);
+            float f0 = bilat_weight<R0>(c0, rec.live && d.live0, d.cpow0, rec, tab, kc);
+            float f1 = bilat_weight<R1>(c1, rec.live && d.live1, d.cpow1, rec, tab, kc);
+            f32x2 f = pk2(f0, f1);
+            d.ws = add2(d.ws, f);
+            d.ax = fma2(f, rec.x, d.ax);
+            d.ay = fma2(f, rec.y, d.ay);
+            d.az = fma2(f, rec.z, d.az);
+            d.aw = fma2(f, rec.w, d.aw);
+        }
+        bilat_duos<S, K, D + 1>::run(rec, duo, tab, kc);
+    }
+};
+template <int S, int K>
+struct bilat_duos<S, K, BW_P / 2> {
+    static __device__ __forceinline__ void run(const bilat_rec &, bilat_duo *,
+                                               const bilat_tab &, const bilat_consts &) {}
+};
+
+// Where window record k of a thread lives: interior blocks add a linear offset, blocks
+// at the edge of the grid clamp each coordinate like the reference's texture fetch.
+// Clamping commutes with sharing: tap r of pixel j and record S j + r + 16 are the
+// same position before the clamp, hence after it.
+template <bool INTERIOR>
+struct bilat_addr {
+    int c0, x, y0, W, H;
+    __device__ __forceinline__ int operator()(const bilat_tab &tab, int k) const {
+        if (INTERIOR) return c0 + tab.loff[k];
+        return clamp_idx(x + tab.off[k].x, y0 + tab.off[k].y, W, H);
+    }
+};
+
+// Loads run BW_AHEAD records in front of the arithmetic (a ring of registers), so that
+// with two or three CTAs per SM the L2 latency hides behind the pairs of earlier records.
+#ifndef BW_AHEAD
+#define BW_AHEAD 2
+#endif
+struct bilat_raw { float4 pix; float2 side; };
+
+template <int K, int KEND, bool INTERIOR>
+__device__ __forceinline__ bilat_raw bilat_load(const float4 *src, const float2 *side,
+                                                const bilat_addr<INTERIOR> &at,
+                                                const bilat_tab &tab) {
+    bilat_raw r;
+    r.pix = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    r.side = make_float2(0.0f, 0.0f);
+    if (K < KEND) {                 // a tap: the whole record
+        const int i = at(tab, K);
+        r.pix = src[i];
+        r.side = side[i];
+    } else if (K == KEND) {         // past the last tap: only its density is read
+        r.pix.w = src[at(tab, K)].w;
+    }
+    return r;
+}
+
+template <int S, int K, int KEND, bool INTERIOR>
+struct bilat_window {
+    // ring[i] holds record K + i, i = 0 .. BW_AHEAD
+    static __device__ __forceinline__ void run(
+            const float4 *src, const float2 *side, const bilat_addr<INTERIOR> &at,
+            float wprev, bilat_raw *ring, bilat_duo *duo, const bilat_tab &tab,
+            const bilat_consts &kc) {
+        const bilat_raw fresh = bilat_load<K + BW_AHEAD + 1, KEND, INTERIOR>(src, side, at, tab);
+        const float4 cur = ring[0].pix;
+        const float2 cs = ring[0].side;
+        bilat_rec rec;
+        rec.live = cur.w > 0.0f;
+        const float pdrcp = 1.0f / cur.w;
+        // the next record's density feeds this record's gradient
+        const float ga = kc.gspeed * ((ring[1].pix.w - wprev) * cs.x);
+        rec.gplus = exp2f(ga);
+        rec.gminus = exp2f(-ga);
+        rec.pow = cs.y;
+        rec.x = pk2(cur.x, cur.x);
+        rec.y = pk2(cur.y, cur.y);
+        rec.z = pk2(cur.z, cur.z);
+        rec.w = pk2(cur.w, cur.w);
+        rec.pdrcp = pk2(pdrcp, pdrcp);
+        bilat_duos<S, K, 0>::run(rec, duo, tab, kc);
+#pragma unroll
+        for (int i = 0; i < BW_AHEAD; i++) ring[i] = ring[i + 1];
+        ring[BW_AHEAD] = fresh;
+        bilat_window<S, K + 1, KEND, INTERIOR>::run(src, side, at, cur.w, ring, duo, tab, kc);
+    }
+};
+template <int S, int KEND, bool INTERIOR>
+struct bilat_window<S, KEND, KEND, INTERIOR> {
+    static __device__ __forceinline__ void run(const float4 *, const float2 *,
+                                               const bilat_addr<INTERIOR> &, float, bilat_raw *,
+                                               bilat_duo *, const bilat_tab &,
+                                               const bilat_consts &) {}
+};
+
+// Per-pixel path with clamped taps (blocks at the edge of the grid); same arithmetic
+// as one pixel of the window, taps r = -15 .. 15 are window records r + 16.
+__device__ __noinline__ void bilat_pixel_clamped(
+        float4 *dst, const float4 *src, const float2 *side, int xi, int yi,
+        const bilat_tab &tab, const bilat_consts &kc, int W, int H) {
+    const int gi = yi * W + xi;
+    const float4 cen = src[gi];
+    const float cpow = side[gi].y;
+    const float cdrcp = 1.0f / (cen.w + 1.0e-6f);
+    const float cnx = cen.x * cdrcp, cny = cen.y * cdrcp, cnz = cen.z * cdrcp;
+    const bool cen_live = cen.w > 0.0f;
+    float ax = 0.0f, ay = 0.0f, az = 0.0f, aw = 0.0f, wsum = 0.0f;
+    auto at = [&](int k) { return clamp_idx(xi + tab.off[k].x, yi + tab.off[k].y, W, H); };
+    float wprev = src[at(0)].w;
+    int ci = at(1);
+    float4 pix = src[ci];
+    float2 ps = side[ci];
+#pragma unroll 1
+    for (int r = -15; r <= 15; r++) {
+        const int ni = at(r + 17);
+        const float4 nxt = src[ni];
+        const float2 ns = side[ni];
+        float yd = pix.x * (1.0f / pix.w) - cnx;
+        float ud = pix.y * (1.0f / pix.w) - cny;
+        float vd = pix.z * (1.0f / pix.w) - cnz;
+        float cdiff = yd * yd + ud * ud + vd * vd;
+        if (!(pix.w > 0.0f && cen_live)) cdiff = 0.5f;
+        float e = kc.dscale * fabsf(cpow - ps.y) + tab.lspa[r < 0 ? -r : r];
+        e += kc.cscale2 * cdiff;
+        const float ga = kc.gspeed * ((nxt.w - wprev) * ps.x);
+        if (r > 0) e -= exp2f(ga);
+        if (r < 0) e -= exp2f(-ga);
+        float f = exp2f(e);
+        wsum += f;
+        ax += f * pix.x;
+        ay += f * pix.y;
+        az += f * pix.z;
+        aw += f * pix.w;
+        wprev = pix.w;
+        pix = nxt;
+        ps = ns;
+    }
+    const float rcp = 1.0f / (wsum + 1e-10f);
+    dst[gi] = make_float4(ax * rcp, ay * rcp, az * rcp, aw * rcp);
+}
+
+// The window of one thread.  Pixels whose sheared position leaves the grid in x belong
+// to the other side of the row (the block shapes tile the row cyclically): the few
+// threads that own such pixels redo them with the per-pixel path.
+template <int S, bool INTERIOR>
+__device__ __forceinline__ void bilat_window_thread(
+        float4 *dst, const float4 *src, const float2 *side, int x, int y0,
+        const bilat_tab &tab, const bilat_consts &kc, int W, int H) {
+    bilat_addr<INTERIOR> at;
+    at.c0 = y0 * W + x; at.x = x; at.y0 = y0; at.W = W; at.H = H;
+    bilat_duo duo[BW_P / 2];
+#pragma unroll
+    for (int d = 0; d < BW_P / 2; d++) {
+        float nc[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int ci = at(tab, S * (2 * d + h) + 16);
+            const float4 cen = src[ci];
+            const float cdrcp = 1.0f / (cen.w + 1.0e-6f);
+            nc[h][0] = -(cen.x * cdrcp); nc[h][1] = -(cen.y * cdrcp); nc[h][2] = -(cen.z * cdrcp);
+            (h ? duo[d].cpow1 : duo[d].cpow0) = side[ci].y;
+            (h ? duo[d].live1 : duo[d].live0) = cen.w > 0.0f;
+        }
+        duo[d].ncx = pk2(nc[0][0], nc[1][0]);
+        duo[d].ncy = pk2(nc[0][1], nc[1][1]);
+        duo[d].ncz = pk2(nc[0][2], nc[1][2]);
+        duo[d].ax = duo[d].ay = duo[d].az = duo[d].aw = duo[d].ws = pk2(0.0f, 0.0f);
+    }
+    constexpr int KEND = 32 + S * (BW_P - 1);      // records 1 .. KEND-1 are taps
+    const float wprev = src[at(tab, 0)].w;
+    bilat_raw ring[BW_AHEAD + 1];
+    ring[0] = bilat_load<1, KEND, INTERIOR>(src, side, at, tab);
+    ring[1] = bilat_load<2, KEND, INTERIOR>(src, side, at, tab);
+#if BW_AHEAD >= 2
+    ring[2] = bilat_load<3, KEND, INTERIOR>(src, side, at, tab);
+#endif
+#if BW_AHEAD >= 3
+    ring[3] = bilat_load<4, KEND, INTERIOR>(src, side, at, tab);
+#endif
+    bilat_window<S, 1, KEND, INTERIOR>::run(src, side, at, wprev, ring, duo, tab, kc);
+#pragma unroll
+    for (int d = 0; d < BW_P / 2; d++) {
+        float ax[2], ay[2], az[2], aw[2], ws[2];
+        unpk2(duo[d].ax, ax[0], ax[1]);
+        unpk2(duo[d].ay, ay[0], ay[1]);
+        unpk2(duo[d].az, az[0], az[1]);
+        unpk2(duo[d].aw, aw[0], aw[1]);
+        unpk2(duo[d].ws, ws[0], ws[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const short2 o = tab.off[S * (2 * d + h) + 16];
+            const int xj = x + o.x, yj = y0 + o.y;
+            if (!INTERIOR && (yj >= H || xj < 0 || xj >= W)) continue;
+            const float rcp = 1.0f / (ws[h] + 1e-10f);
+            dst[yj * W + xj] = make_float4(ax[h] * rcp, ay[h] * rcp, az[h] * rcp, aw[h] * rcp);
+        }
+    }
+    if (!INTERIOR) {
+#pragma unroll 1
+        for (int j = 0; j < BW_P; j++) {
+            const short2 o = tab.off[S * j + 16];
+            const int xj = x + o.x, yj = y0 + o.y;
+            if (yj < H && (xj < 0 || xj >= W))
+                bilat_pixel_clamped(dst, src, side, xj < 0 ? xj + W : xj - W, yj, tab, kc, W, H);
+        }
+    }
+}
+
+#ifndef BW_MIN_CTAS
+#define BW_MIN_CTAS 2          // 128 registers: the window state fits without spills
+#endif
+template <int S>
+__global__ void __launch_bounds__(256, BW_MIN_CTAS)
+k_bilateral_window(float4 *dst, const float4 *src, const float2 *side,
+                   const __grid_constant__ bilat_tab tab, bilat_consts kc, cb_dims dim) {
+    const int W = dim.astride, H = dim.aheight;
+    const int x0 = blockIdx.x * 32, yb = blockIdx.y * 32;
+    const int x = x0 + threadIdx.x;
+    // first row of this thread: S = 1 -> rows y0 .. y0+3; S = 4 -> rows y0, y0+4, ...
+    const int y0 = S == 1 ? yb + threadIdx.y * BW_P
+                          : yb + (threadIdx.y >> 2) * 16 + (threadIdx.y & 3);
+    const bool interior = x0 + tab.xlo >= 0 && x0 + 31 + tab.xhi < W &&
+                          yb + tab.ylo >= 0 && yb + 31 + tab.yhi < H;
+    if (interior)
+        bilat_window_thread<S, true>(dst, src, side, x, y0, tab, kc, W, H);
+    else if (y0 < H)
+        bilat_window_thread<S, false>(dst, src, side, x, y0, tab, kc, W, H);
+}
+
+// Host copy of the first eight entries of c_dirs, for the window tables.
+static const float h_dirs[8][2] = {
+    {1.0f, 0.0f},  {0.0f, 1.0f},  {1.0f, 1.0f},  {-1.0f, 1.0f},
+    {1.0f, 0.5f},  {-0.5f, 1.0f}, {1.0f, -0.5f}, {0.5f, 1.0f},
+};
+
+// Window step of a direction: 1 or 4 for the y-major directions handled by
+// k_bilateral_window, 0 for the others.
+static int bilat_window_step(int pattern) {
+    if (pattern == 1 || pattern == 2 || pattern == 3) return 1;
+    if (pattern == 5 || pattern == 7) return 4;
+    return 0;
+}
+
+static bilat_tab make_bilat_tab(int pattern, int step, float sstd, int astride) {
+    bilat_tab t;
+    memset(&t, 0, sizeof(t));
+    const float log2e = 1.44269502162933f;
+    for (int r = 0; r < 16; r++)
+        t.lspa[r] = log2e * (float)(r * r) / (-K_SQRT2 * sstd);
+    const int nrec = 33 + step * (BW_P - 1);
+    for (int k = 0; k < nrec; k++) {
+        // shear_offset on the host: float product, round to nearest even
+        const float s = (float)(k - 16);
+        const int dx = (int)nearbyintf(h_dirs[pattern][0] * s);
+        const int dy = (int)nearbyintf(h_dirs[pattern][1] * s);
+        t.off[k] = make_short2((short)dx, (short)dy);
+        t.loff[k] = dy * astride + dx;
+        t.xlo = dx < t.xlo ? dx : t.xlo;
+        t.xhi = dx > t.xhi ? dx : t.xhi;
+        t.ylo = dy < t.ylo ? dy : t.ylo;
+        t.yhi = dy > t.yhi ? dy : t.yhi;
+    }
+    return t;
+}
+
 // ---- C ABI -------------------------------------------------------------------
 static inline int nbins(const cb_dims *d) { return d->aheight * d->astride; }
 static inline dim3 grid2(const cb_dims *d) { return dim3(d->astride / 32, d->aheight / 8); }
@@ -711,7 +1076,21 @@ int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4, int pat
     CB_LAUNCH_CHECK();
     k_bilat_prep2<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
     CB_LAUNCH_CHECK();
-    if (radius == 15)       // the reference's fixed radius (cuburn/filters.py:59): unrolled
+    const int step = radius == 15 ? bilat_window_step(pattern) : 0;
+    if (step) {
+        const bilat_tab tab = make_bilat_tab(pattern, step, sstd, dim->astride);
+        bilat_consts kc;
+        kc.cscale2 = 1.44269502162933f / (-K_SQRT2 * 3.0f * cstd);
+        kc.dscale = -0.5f / dstd;
+        kc.gspeed = gspeed;
+        const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
+        if (step == 1)
+            k_bilateral_window<1><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(
+                cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, tab, kc, *dim);
+        else
+            k_bilateral_window<4><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(
+                cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, tab, kc, *dim);
+    } else if (radius == 15)  // the reference's fixed radius (cuburn/filters.py:59): unrolled
         k_bilateral_fast<15><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
             cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
             cstd, dstd, gspeed, *dim);

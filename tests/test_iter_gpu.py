@@ -389,8 +389,15 @@ def test_max_knots_and_palettes(native, built):
 def test_packed_accumulation_equals_float4(native, built):
     """The packed u64 path (reference format a15 + overflow spill + flush, used for grids
     far beyond L2) and the float4 path see the same sample set for the same seeds: the
-    density channel is identical, colour sums agree to float rounding -- including bins
-    that overflowed the 10-bit counter many times."""
+    density channel is identical, colour sums agree to float32 accumulation error --
+    including bins that overflowed the 10-bit counter many times.
+
+    The float4 path adds every sample to a float32 running sum (round to nearest in the
+    L2 reduction unit, tools/micro/red_rounding.py); with n adds of nearly equal values the
+    rounding errors do not average out, so its relative error is bounded by n * 2^-25,
+    not by sqrt(n).  The packed path adds 8-bit integers exactly and touches the float
+    histogram once per ~32 samples, so it is the more exact of the two in very hot bins
+    (here up to ~6e5 samples per bin: measured 6e-3 against a 1.7e-2 bound)."""
     N = native
     from cuburn_b200 import samples, render
     gnm = samples.g3()
@@ -412,11 +419,13 @@ def test_packed_accumulation_equals_float4(native, built):
     assert a[..., 3].max() > 100000                      # far beyond 1023: many spills
     assert np.array_equal(a[..., 3], b[..., 3])
     m = a[..., 3] > 0
-    # colour sums: the packed path adds 8-bit integers exactly (up to 1023 at a time),
-    # the float4 path accumulates ~1e5 float32 terms in the hottest bins
+    bound = 1e-4 + a[..., 3][m].astype(np.float64) * 2.0 ** -25
     for ch in range(3):
         rel = np.abs(a[..., ch][m] - b[..., ch][m]) / np.maximum(a[..., ch][m], 1e-3)
-        assert rel.max() < 2e-3, (ch, float(rel.max()))
+        assert (rel <= bound).all(), (ch, float((rel / bound).max()))
+        # and bins of ordinary density agree far better than that
+        cool = a[..., 3][m] < 20000
+        assert rel[cool].max() < 1e-3, (ch, float(rel[cool].max()))
     assert float(b[..., 3].sum()) <= w * h * spp
 
 
