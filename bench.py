@@ -41,6 +41,10 @@ WORKLOADS = {
     # BASELINE.json configs[2]: one 4K frame at 4000 spp split over the GPUs (strong)
     'still4k': dict(genome='G6F', width=3840, height=2160, spp=4000, scaling='strong',
                     label='3840x2160 still, G6F, 4000 spp in total, samples split over the GPUs'),
+    # BASELINE.json configs[4]: 8K, 24 heavy xforms; the 512 MiB histogram does not fit L2
+    'still8k': dict(genome='G24H', width=7680, height=4320, spp=2000, scaling='strong',
+                    label='7680x4320 still, G24H (24 xforms, heavy variations), 2000 spp in '
+                          'total, samples split over the GPUs'),
 }
 CONFIG = dict(WORKLOADS['still1080'])
 # profiles/r01_final_cb_iter.md (ncu --set full, still1080 workload): 37.66 MB read +
@@ -347,7 +351,9 @@ def main():
     # ---- roofline of the dominant kernel (cb_iter) -----------------------------------
     peak, peak_src = read_peaks()
     iter_ms_mean = iter_total / args.steps
-    algo_bytes = 16.0 * mine                     # one 16-byte float4 accumulate per sample
+    packed = rmgr._use_packed(dim.ah * dim.astride)
+    # one 16-byte float4 accumulate per sample (8-byte packed cell beyond 1.5 x L2)
+    algo_bytes = (8.0 if packed else 16.0) * mine
     achieved = algo_bytes / (iter_ms_mean * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': 'cb_iter', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
@@ -368,7 +374,10 @@ def main():
         'frac': kernel_rate / red_peak}
     # dram__bytes_read.sum + dram__bytes_write.sum of one cb_iter launch, from the
     # committed ncu capture (profiles/); None until a capture exists for this kernel
-    roofline['traffic'] = NCU_DRAM_BYTES_PER_LAUNCH
+    roofline['traffic'] = NCU_DRAM_BYTES_PER_LAUNCH if args.workload == 'still1080' else None
+    if packed:
+        roofline['note'] = ('algorithmic bytes = 8 B packed-u64 accumulate per sample; the grid is '
+                            'far larger than L2, so the bound is HBM sector read-modify-write')
     filt_ms = ms_per_step - iter_ms_mean
     roofline_filters = {'bound': 'hbm', 'stage': 'interp + filter chain + convert',
                         'algorithmic_bytes_per_bin': 804,
