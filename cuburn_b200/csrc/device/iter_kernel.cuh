@@ -159,15 +159,26 @@ __device__ __forceinline__ int exchange_slot(int tid, int warp, int lane, int ro
 #endif
 }
 
-// Apply one round of the chaos game to this thread's point and swap points
-// across the CTA.  `round` only steers the permutation.
-__device__ __forceinline__ unsigned int chaos_round(xchg_buf *xb, int tid, int warp, int lane,
-                                                    int round, float &x, float &y, float &c,
-                                                    mwc_st &rng) {
+// ---- one round = push, record, pull ------------------------------------------------
+// A round transforms the point, hands it to another thread of the CTA (push ... barrier
+// ... pull) and records one sample.  The sample recorded is the point the thread just
+// produced, not the one it receives (every transformed point is still recorded exactly
+// once): its coordinates are dead once published, so the final xform and the camera run
+// without the trajectory in registers.  Where the reduction is issued relative to the
+// barrier is a per-genome choice (RED_BEFORE_PULL, set by the code generator): a barrier
+// right behind a global reduction waits for its L2 round trip, which paces the
+// reductions of heavy genomes usefully (-3 % G6F, -2..9 % G24H: the warps of a CTA run
+// different xforms and reach the barrier spread out) and starves light ones whose warps
+// run in lockstep (+11..16 % G3), see profiles/r01_iter_variants.md.  A split-phase
+// mbarrier (arrive, record, wait) was measured too: its polling wait costs more issue
+// slots than the barrier stall it removes (25.0 vs 23.4 ms, G6F).
+// First half of a round: transform this thread's point and publish it.  Returns the
+// warp's random word (its low bits pick the lane that drains packed cells).
+__device__ __forceinline__ unsigned int chaos_push(xchg_buf *xb, int tid, int warp, int lane, int round,
+                                                   float &x, float &y, float &c, mwc_st &rng) {
     if (point_is_bad(x, y)) reseed_point(x, y, c, rng);
 
-    // one random word per warp per round (iter.py:197-201,261): its value picks the
-    // xform, its low bits decide whether this round checks for cell overflow
+    // one random word per warp per round (iter.py:197-201,261)
     unsigned int word = 0;
     if (lane == 0) word = mwc_next(rng);
     word = __shfl_sync(0xffffffffu, word, 0);
@@ -178,12 +189,35 @@ __device__ __forceinline__ unsigned int chaos_round(xchg_buf *xb, int tid, int w
     int slot = exchange_slot(tid, warp, lane, round);
     b->xy[slot] = make_float2(x, y);
     b->c[slot] = c;
+    return word;
+}
+
+// Second half: take the point another thread published this round.
+__device__ __forceinline__ void chaos_pull(xchg_buf *xb, int tid, int round, float &x, float &y, float &c) {
     __syncthreads();
+    xchg_buf *b = xb + (round & 1);
     float2 p = b->xy[tid];
     x = p.x;
     y = p.y;
     c = b->c[tid];
-    return word;
+}
+
+#if ACC_PACKED
+typedef unsigned long long pal_entry;
+#else
+typedef float4 pal_entry;
+#endif
+#ifndef RED_BEFORE_PULL
+#define RED_BEFORE_PULL 0
+#endif
+
+__device__ __forceinline__ void record_sample(const iter_args &a, int bin, pal_entry col,
+                                              unsigned int word, int lane) {
+#if ACC_PACKED
+    accumulate_packed(a.cells + bin, a.hist + bin, col, (word & 31u) == (unsigned int)lane);
+#else
+    red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), col);
+#endif
 }
 
 extern "C" __global__ void __launch_bounds__(ITER_THREADS, ITER_MIN_CTAS)
@@ -239,8 +273,10 @@ cb_iter(const __grid_constant__ iter_args a) {
 
         if (fresh) {
             // settle new trajectories without recording them (iter.py:211-216)
-            for (int r = 0; r < a.fuse_rounds; r++, round_ctr++)
-                chaos_round(xb, tid, warp, lane, round_ctr, x, y, c, rng);
+            for (int r = 0; r < a.fuse_rounds; r++, round_ctr++) {
+                chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, rng);
+                chaos_pull(xb, tid, round_ctr, x, y, c);
+            }
             fresh = false;
             if (lu >= nunits) break;
         }
@@ -254,21 +290,26 @@ cb_iter(const __grid_constant__ iter_args a) {
         const float color_dither = 0.49f * mwc_next_11(rng);      // iter.py:185
 
         for (int r = 0; r < rounds; r++, round_ctr++) {
-            unsigned int word = chaos_round(xb, tid, warp, lane, round_ctr, x, y, c, rng);
-            if (r * ITER_THREADS + tid >= live) continue;
-
-            float fx = x, fy = y, fc = c;
+            unsigned int word = chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, rng);
+            // The sample of the point this thread just produced.  Its coordinates are
+            // dead once published (the thread continues with the point it receives), so
+            // the final xform and the camera run with x, y, c off the register file.
+            int bin = -1;
+            unsigned int cidx = 0;
+            if (r * ITER_THREADS + tid < live) {
+                float fx = x, fy = y, fc = c;
 #if HAS_FINAL
-            final_step(fx, fy, fc, rng);
+                final_step(fx, fy, fc, rng);
 #endif
-            int bin = sample_bin(fx, fy, a.dim.astride, a.dim.aheight);
-            if (bin < 0) continue;
-#if ACC_PACKED
-            accumulate_packed(a.cells + bin, a.hist + bin, s_pal[color_index(fc, color_dither)],
-                              (word & 31u) == (unsigned int)lane);
+                bin = sample_bin(fx, fy, a.dim.astride, a.dim.aheight);
+                cidx = color_index(fc, color_dither);
+            }
+#if RED_BEFORE_PULL
+            if (bin >= 0) record_sample(a, bin, s_pal[cidx], word, lane);
+            chaos_pull(xb, tid, round_ctr, x, y, c);
 #else
-            float4 col = s_pal[color_index(fc, color_dither)];
-            red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), col);
+            chaos_pull(xb, tid, round_ctr, x, y, c);
+            if (bin >= 0) record_sample(a, bin, s_pal[cidx], word, lane);
 #endif
         }
     }
