@@ -178,6 +178,7 @@ class GenomePacker(object):
         times.fill(1e9)
         knots.fill(0)
         scale = gnm.get('time', {}).get('duration', 1)
+        const_rows, const_vals = [], []
         for idx, path in enumerate(self.row_paths):
             attr = gnm
             for name in path:
@@ -185,6 +186,12 @@ class GenomePacker(object):
                     attr = resolve_spec(self.spec, path).default
                     break
                 attr = attr[name]
+            if type(attr) in (int, float):
+                # a constant normalises to four equal knots at t = -2, 0, 1, 3; rows
+                # like this are most of a genome and are written in one go below
+                const_rows.append(idx)
+                const_vals.append(attr)
+                continue
             kn = SplineEval.normalize(attr, scale)
             n = kn.shape[1]
             if n > MAX_KNOTS:
@@ -192,4 +199,7 @@ class GenomePacker(object):
                                  % ('.'.join(path), n, MAX_KNOTS))
             times[idx, :n] = kn[0]
             knots[idx, :n] = kn[1]
+        if const_rows:
+            times[const_rows, :4] = (-2.0, 0.0, 1.0, 3.0)
+            knots[const_rows, :4] = np.asarray(const_vals, np.float64)[:, None]
         return times, knots
