@@ -47,10 +47,10 @@ WORKLOADS = {
                           'total, samples split over the GPUs'),
 }
 CONFIG = dict(WORKLOADS['still1080'])
-# profiles/r01_final_cb_iter.md (ncu --set full, still1080 workload): 37.66 MB read +
-# 0.86 MB written per cb_iter launch -- the first touch of the histogram; the 66 GB of
+# profiles/r01_final_cb_iter.md (ncu --set full, still1080 workload): 37.69 MB read +
+# 0.20 MB written per cb_iter launch -- the first touch of the histogram; the 66 GB of
 # atomic payload never leaves L2
-NCU_DRAM_BYTES_PER_LAUNCH = 38.5e6
+NCU_DRAM_BYTES_PER_LAUNCH = 37.9e6
 UNIT = 65536
 
 
