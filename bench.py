@@ -222,6 +222,9 @@ def main():
     ap.add_argument('--filter-shard', default='band', choices=['band', 'root'],
                     help='multi-GPU: filter row bands on every GPU (all-reduce + gather) '
                          'or the whole frame on the root (reduce)')
+    ap.add_argument('--collectives', default='torch', choices=['torch', 'native'],
+                    help="multi-GPU exchange through torch.distributed or through the "
+                         "library's own NCCL communicator (cb_hist_reduce / cb_band_gather)")
     ap.add_argument('--workload', default='still1080', choices=sorted(WORKLOADS),
                     help='still1080 = BASELINE configs[1] (default); still4k = configs[2]')
     args = ap.parse_args()
@@ -249,10 +252,11 @@ def main():
     reducer = None
     if n_gpus > 1:
         banded = args.filter_shard == 'band'
-        reducer = multigpu.HistReducer(root=None if banded else 0)
+        comm = multigpu.NativeComm(rank, n_gpus) if args.collectives == 'native' else None
+        reducer = multigpu.HistReducer(root=None if banded else 0, comm=comm)
         rmgr.hist_hook = reducer
         if banded:
-            rmgr.band_filter = multigpu.BandFilter(rank, n_gpus, root=0)
+            rmgr.band_filter = multigpu.BandFilter(rank, n_gpus, root=0, comm=comm or True)
     dim = rmgr.fb.set_dim(gprof.width, gprof.height)
     td = gprof.frame_width(tc) / round(gprof.fps * gprof.duration)
     ts = tc - 0.5 * td
@@ -404,6 +408,7 @@ def main():
                    'samples_per_step': total, 'frames_per_second': 1e3 / ms_per_step,
                    'l2': 'L2 flushed between timed steps (512 MiB fill)',
                    'timing': 'CUDA events on the launching stream, per step, max over ranks',
+                   'collectives': args.collectives if n_gpus > 1 else None,
                    'parallelism': ('single GPU' if n_gpus == 1 else
                                    'independent RNG streams per GPU + NCCL all-reduce; filter '
                                    'chain sharded by row bands, gathered on the root'

@@ -136,6 +136,13 @@ _SIGNATURES = {
     'cb_convert': (c_int, [c_int, c_uint64, c_uint64, c_int, POINTER(Dims), c_uint64,
                            c_int, c_void_p]),
     'cb_convert_size': (c_int, [c_int, POINTER(Dims), POINTER(c_size_t)]),
+    'cb_comm_version': (c_int, [POINTER(c_int)]),
+    'cb_comm_unique_id': (c_int, [POINTER(ctypes.c_uint8)]),
+    'cb_comm_create': (c_int, [POINTER(ctypes.c_uint8), c_int, c_int, POINTER(c_void_p)]),
+    'cb_comm_destroy': (c_int, [c_void_p]),
+    'cb_hist_reduce': (c_int, [c_void_p, c_uint64, POINTER(Dims), c_int, c_void_p]),
+    'cb_band_rows': (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    'cb_band_gather': (c_int, [c_void_p, c_uint64, POINTER(Dims), c_int, c_void_p]),
 }
 
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -27,6 +27,7 @@ SOURCES = [
     ('cb_module.cu', []),
     ('cb_filters.cu', ['-use_fast_math']),
     ('cb_output.cu', ['-fmad=false']),
+    ('cb_comm.cu', []),
 ]
 
 

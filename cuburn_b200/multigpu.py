@@ -79,16 +79,66 @@ def make_rank_seeds(rank, world, host_seed, nstreams=262144):
     return seeds
 
 
+class NativeComm(object):
+    """
+    The library's own NCCL communicator (cb_comm_*): the exchange steps then run as
+    C-ABI calls on the renderer's stream, and torch.distributed is only the courier
+    for the 128-byte unique id (any backend; a file or a socket would do as well).
+    """
+    def __init__(self, rank=None, world=None, exchange_id=None):
+        import ctypes
+        from . import _native as N
+        env_rank, env_world, _ = env_rank_world()
+        self.rank = env_rank if rank is None else rank
+        self.world = env_world if world is None else world
+        N.ensure_init()
+        ident = (ctypes.c_uint8 * 128)()
+        if self.rank == 0:
+            N.check(N.lib().cb_comm_unique_id(ident))
+        raw = bytes(ident)
+        if self.world > 1:
+            raw = (exchange_id or self._broadcast)(raw)
+        ident = (ctypes.c_uint8 * 128)(*raw)
+        handle = ctypes.c_void_p()
+        N.check(N.lib().cb_comm_create(ident, self.rank, self.world, ctypes.byref(handle)))
+        self.handle, self._N = handle, N
+
+    @staticmethod
+    def _broadcast(raw):
+        import torch.distributed as dist
+        box = [raw]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def hist_reduce(self, buf, dim, root, stream):
+        """root: a rank, or None for every rank (all-reduce)."""
+        N = self._N
+        N.check(N.lib().cb_hist_reduce(self.handle, int(buf), N.byref(dim),
+                                       -1 if root is None else root, stream.handle))
+
+    def band_gather(self, buf, dim, root, stream):
+        N = self._N
+        N.check(N.lib().cb_band_gather(self.handle, int(buf), N.byref(dim), root, stream.handle))
+
+    def close(self):
+        if self.handle:
+            self._N.check(self._N.lib().cb_comm_destroy(self.handle))
+            self.handle = None
+
+
 class HistReducer(object):
     """
     ``RenderManager.hist_hook``: sums the per-GPU float4 histograms onto
     ``root`` before the filter chain runs there; ``root=None`` leaves the sum on
     every GPU (all-reduce), which ``BandFilter`` needs.
     """
-    def __init__(self, root=0):
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist, self.root = torch, dist, root
+    def __init__(self, root=0, comm=None):
+        """comm: a NativeComm to run the collective through the C ABI; None = torch."""
+        self.root, self.comm = root, comm
+        if comm is None:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
         self._events = []
 
     def tensor_view(self, buf, nfloats):
@@ -96,6 +146,13 @@ class HistReducer(object):
         return self.torch.as_tensor(view, device='cuda')
 
     def __call__(self, fb, dim, stream):
+        if self.comm is not None:
+            from . import _native as N
+            e0, e1 = N.Event().record(stream), N.Event()
+            self.comm.hist_reduce(fb.d_front, dim, self.root, stream)
+            e1.record(stream)
+            self._events.append((e0, e1))
+            return
         if not self.dist.is_initialized() or self.dist.get_world_size() == 1:
             return
         torch = self.torch
@@ -117,7 +174,12 @@ class HistReducer(object):
     def mean_reduce_ms(self, last=None):
         """Device time of the recorded reduces (call after a synchronize)."""
         evs = self._events[-last:] if last else self._events
-        return float(np.mean([a.elapsed_time(b) for a, b in evs])) if evs else None
+        return float(np.mean([_elapsed(a, b) for a, b in evs])) if evs else None
+
+
+def _elapsed(e0, e1):
+    """ms between two recorded events (torch.cuda.Event or the library's Event)."""
+    return e0.elapsed_time(e1) if hasattr(e0, 'elapsed_time') else e1.time_since(e0)
 
 
 def band_rows(aheight, rank, world):
@@ -150,8 +212,10 @@ class BandFilter(object):
     used; the band itself is bit-identical to the single-GPU result.
     """
     def __init__(self, rank, world, root=0, comm=True):
+        """comm: True = torch.distributed gather, a NativeComm = cb_band_gather through
+        the C ABI, False = no exchange (one process playing a rank, for tests)."""
         self.rank, self.world, self.root, self.comm = rank, world, root, comm
-        if comm:
+        if comm is True:
             import torch
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
@@ -171,6 +235,13 @@ class BandFilter(object):
         row0, row1 = self.filter_band(fb, filts, gprof, dim, tc, stream)
         if not self.comm or self.world == 1:
             return
+        if self.comm is not True:
+            from . import _native as N
+            e0, e1 = N.Event().record(stream), N.Event()
+            self.comm.band_gather(fb.d_front, dim, self.root, stream)
+            e1.record(stream)
+            self._events.append((e0, e1))
+            return
         torch, dist = self.torch, self.dist
         full = torch.as_tensor(fb.d_front.view((dim.ah, 4 * dim.astride), '<f4'), device='cuda')
         ext = torch.cuda.ExternalStream(stream.handle.value)
@@ -188,7 +259,7 @@ class BandFilter(object):
 
     def mean_gather_ms(self, last=None):
         evs = self._events[-last:] if last else self._events
-        return float(np.mean([a.elapsed_time(b) for a, b in evs])) if evs else None
+        return float(np.mean([_elapsed(a, b) for a, b in evs])) if evs else None
 
 
 def gather_host_bands(frame, rank, world, root=0):

@@ -31,6 +31,7 @@ typedef uint64_t cb_dptr;
 typedef struct cb_stream_s *cb_stream;
 typedef struct cb_event_s *cb_event;
 typedef struct cb_module_s *cb_module;
+typedef struct cb_comm_s *cb_comm;
 
 typedef enum {
     CB_OK = 0,
@@ -230,6 +231,34 @@ typedef enum {
 int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
                const cb_dims *dim, cb_dptr seeds, int nstreams, cb_stream s);
 int cb_convert_size(cb_pixfmt fmt, const cb_dims *dim, size_t *bytes);
+
+/* ---- multi-GPU exchange (one process per GPU, NCCL over NVLink) ----------
+ * The reference ships whole frames between worker processes
+ * (distribute.py:131-248) and has no device-side exchange.  A still split over
+ * GPUs by samples needs one: the sum of the per-GPU histograms, and, when the
+ * filter chain is sharded by rows too, the gather of the filtered bands.  NCCL
+ * is bound at run time; without it these return CB_ERR_INVALID with a message.
+ * Calls are stream-ordered on `s` like everything else. */
+#define CB_COMM_ID_BYTES 128
+int cb_comm_version(int *version);                       /* NCCL_VERSION_CODE */
+/* One rank creates the id, every rank receives it out of band (file, socket,
+ * torch.distributed ...) and joins with its rank. */
+int cb_comm_unique_id(uint8_t id[CB_COMM_ID_BYTES]);
+int cb_comm_create(const uint8_t id[CB_COMM_ID_BYTES], int rank, int world,
+                   cb_comm *comm);
+int cb_comm_destroy(cb_comm comm);
+/* hist4 (float4 [aheight][astride]) += the other ranks' histograms, in place:
+ * on `root` only, or on every rank when root = -1. */
+int cb_hist_reduce(cb_comm comm, cb_dptr hist4, const cb_dims *dim, int root,
+                   cb_stream s);
+/* Rows [row0, row1) of the accumulation grid that `rank` filters: equally tall
+ * bands, multiples of 16 rows; the last bands slide up (and overlap their
+ * neighbour) when aheight does not divide. */
+int cb_band_rows(int aheight, int rank, int world, int *row0, int *row1);
+/* Collect every rank's band of frame4 (float4 [aheight][astride]) in root's
+ * copy; a rank's own band must already be in place. */
+int cb_band_gather(cb_comm comm, cb_dptr frame4, const cb_dims *dim, int root,
+                   cb_stream s);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,47 @@ def test_band_rows_cover_the_grid_with_equal_bands():
             assert bands[0][0] == 0 and bands[-1][1] == ah
 
 
+def test_c_abi_band_rows_match_the_host_mirror(built):
+    import ctypes
+    from cuburn_b200 import _native as N, multigpu
+    L = N.lib()
+    r0, r1 = ctypes.c_int(), ctypes.c_int()
+    for ah in (16, 208, 384, 752, 1104, 2192, 4352):
+        for world in (1, 2, 3, 4, 8):
+            for rank in range(world):
+                N.check(L.cb_band_rows(ah, rank, world, ctypes.byref(r0), ctypes.byref(r1)))
+                assert (r0.value, r1.value) == multigpu.band_rows(ah, rank, world)
+    assert L.cb_band_rows(100, 0, 1, ctypes.byref(r0), ctypes.byref(r1)) == N.CB_ERR_INVALID
+    assert L.cb_band_rows(208, 2, 2, ctypes.byref(r0), ctypes.byref(r1)) == N.CB_ERR_INVALID
+    # the exchange entry points refuse a null communicator instead of crashing
+    dim = N.calc_dim(320, 180)
+    assert L.cb_hist_reduce(None, 16, N.byref(dim), 0, None) == N.CB_ERR_INVALID
+    assert L.cb_band_gather(None, 16, N.byref(dim), 0, None) == N.CB_ERR_INVALID
+    ver = ctypes.c_int()
+    if L.cb_comm_version(ctypes.byref(ver)) == 0:       # NCCL present on this box
+        assert ver.value >= 21800
+
+
+@pytest.mark.gpu
+def test_native_comm_world1_is_the_identity(native, built):
+    """cb_comm_* on one GPU: a one-rank NCCL communicator, reduce / all-reduce leave
+    the histogram as it is and the band gather has nothing to move."""
+    N = native
+    from cuburn_b200 import multigpu, render
+    comm = multigpu.NativeComm(rank=0, world=1)
+    fb = render.Framebuffers(seed=1)
+    dim = fb.set_dim(320, 180)
+    hist = np.random.RandomState(3).rand(dim.ah, dim.astride, 4).astype(np.float32)
+    s = N.Stream()
+    N.memcpy_htod(fb.d_front, hist, s)
+    for root in (0, None):
+        multigpu.HistReducer(root=root, comm=comm)(fb, dim, s)
+    comm.band_gather(fb.d_front, dim, 0, s)
+    s.synchronize()
+    assert np.array_equal(N.from_device(fb.d_front, hist.shape, np.float32), hist)
+    comm.close()
+
+
 def _chain_and_profile():
     from cuburn_b200 import samples, profile, filters
     gnm = samples.g3()

@@ -28,10 +28,11 @@ shape = (dim.ah, dim.astride, 4)
 rmgr._copy(rdr, gnm)
 rmgr._interp(rdr, gnm, dim, tc, 0.0)
 rmgr._iter(rdr, gnm, gprof, dim, tc)
-multigpu.HistReducer(root=None)(rmgr.fb, dim, s)
+comm = multigpu.NativeComm(rank, world) if os.environ.get('COLLECTIVES') == 'native' else None
+multigpu.HistReducer(root=None, comm=comm)(rmgr.fb, dim, s)
 s.synchronize()
 hist = N.from_device(rmgr.fb.d_front, shape, np.float32)
-rmgr.band_filter = multigpu.BandFilter(rank, world, root=0)
+rmgr.band_filter = multigpu.BandFilter(rank, world, root=0, comm=comm or True)
 rmgr._filter(rdr, gprof, dim, tc)
 s.synchronize()
 banded = N.from_device(rmgr.fb.d_front, shape, np.float32)
@@ -44,6 +45,7 @@ if rank == 0:
     whole = N.from_device(rmgr.fb.d_front, shape, np.float32)
     same = banded.view(np.uint32) == whole.view(np.uint32)
     print(json.dumps({'world': world, 'frame': [w, h, spp],
+                      'collectives': 'native (cb_hist_reduce, cb_band_gather)' if comm else 'torch.distributed',
                       'halo_rows': multigpu.chain_reach(rdr.filts, gprof, tc),
                       'bands': [multigpu.band_rows(dim.ah, r, world) for r in range(world)],
                       'samples_in_histogram': float(hist[..., 3].sum()),
