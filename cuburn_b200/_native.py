@@ -282,6 +282,26 @@ class DeviceBuffer(object):
         return _CudaArrayView(self, shape, typestr)
 
 
+def preload_nccl():
+    """
+    Make sure the NCCL this process ends up with is the one PyTorch ships, when PyTorch
+    is installed: libtorch_cuda needs symbols of its own NCCL version, and the dynamic
+    loader keeps whichever ``libnccl.so.2`` arrives first.  Call before the first
+    ``cb_comm_*`` (``multigpu.NativeComm`` does).  Returns the path loaded, or None.
+    """
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec('nvidia.nccl')
+    except (ImportError, ValueError):
+        spec = None
+    for base in (spec.submodule_search_locations if spec else []):
+        path = os.path.join(base, 'lib', 'libnccl.so.2')
+        if os.path.exists(path):
+            ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+            return path
+    return None
+
+
 class DeviceSlice(object):
     """A window into someone else's allocation (never freed here)."""
     def __init__(self, buf, offset, nbytes):

@@ -4,9 +4,9 @@
 // The reference has no multi-GPU data path (its job farm ships whole frames between
 // processes, distribute.py:131-248); these entry points are what SURVEY 8(b)/(e) ask
 // of a drop-in: `hist_reduce(comm, root)` on the caller's stream.  NCCL is bound at
-// run time (dlopen of libnccl.so.2: the copy the process already loaded, e.g.
-// PyTorch's, or the system one), so the library still loads on a box without it.
+// run time (dlopen of libnccl.so.2), so the library still loads on a box without it.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <nccl.h>
@@ -42,8 +42,14 @@ bool bind(F &fn, const char *name) {
 
 int load_nccl() {
     if (g_nccl.lib) return CB_OK;
-    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // One process must not end up with two NCCLs under the same soname: take the copy
+    // that is already loaded (PyTorch's, if the host imported it first), else the one
+    // named by CUBURN_B200_NCCL, else the system's.
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    const char *path = getenv("CUBURN_B200_NCCL");
+    if (!lib && path && *path) lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!lib) {
         cb_set_error("NCCL is not available: %s", dlerror());
         return CB_ERR_INVALID;

@@ -390,29 +390,60 @@ k_bilateral(float4 *dst, const float4 *src, const float *blur, int pattern,
 //                  - [r != 0] exp2(gspeed * grad) )
 // Prologue 1: aux[i].x = 7-tap blur of density (as den_blur), aux[i].y = w^dpow.
 // Prologue 2: side[i] = (1 / (two-octave blur + 1e-6), w^dpow)  (den_blur_1c, up = 1)
+// Both prologues are short and latency-bound, so a thread handles PREP_PER pixels
+// (rows 8 apart in a 32 x 32 tile) and issues all of their loads before it uses any.
+#define PREP_PER 4
 __global__ void __launch_bounds__(256)
 k_bilat_prep1(float2 *aux, const float4 *src, int pattern, coefs7 k, float dpow,
               cb_dims dim) {
-    PIX_XY();
-    float den = 0.0f;
+    const int xi = blockIdx.x * 32 + threadIdx.x;
+    const int y0 = blockIdx.y * (8 * PREP_PER) + threadIdx.y;
+    float w[PREP_PER][7], cw[PREP_PER];
 #pragma unroll
-    for (int i = 0; i < 7; i++) {
-        int2 o = shear_offset(pattern, (float)(i - 3));
-        den += src[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].w * k.c[i];
+    for (int p = 0; p < PREP_PER; p++) {
+        const int yi = min(y0 + 8 * p, dim.aheight - 1);
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            int2 o = shear_offset(pattern, (float)(i - 3));
+            w[p][i] = src[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].w;
+        }
+        cw[p] = src[yi * dim.astride + xi].w;
     }
-    aux[gi] = make_float2(den, powf(src[gi].w, dpow));
+#pragma unroll
+    for (int p = 0; p < PREP_PER; p++) {
+        const int yi = y0 + 8 * p;
+        if (yi >= dim.aheight) break;
+        float den = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 7; i++) den += w[p][i] * k.c[i];
+        aux[yi * dim.astride + xi] = make_float2(den, powf(cw[p], dpow));
+    }
 }
 
 __global__ void __launch_bounds__(256)
 k_bilat_prep2(float2 *side, const float2 *aux, int pattern, coefs7 k, cb_dims dim) {
-    PIX_XY();
-    float den = 0.0f;
+    const int xi = blockIdx.x * 32 + threadIdx.x;
+    const int y0 = blockIdx.y * (8 * PREP_PER) + threadIdx.y;
+    float d[PREP_PER][7], cp[PREP_PER];
 #pragma unroll
-    for (int i = 0; i < 7; i++) {
-        int2 o = shear_offset(pattern, (float)((i - 3) * 2));
-        den += aux[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].x * k.c[i];
+    for (int p = 0; p < PREP_PER; p++) {
+        const int yi = min(y0 + 8 * p, dim.aheight - 1);
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            int2 o = shear_offset(pattern, (float)((i - 3) * 2));
+            d[p][i] = aux[clamp_idx(xi + o.x, yi + o.y, dim.astride, dim.aheight)].x;
+        }
+        cp[p] = aux[yi * dim.astride + xi].y;
     }
-    side[gi] = make_float2(1.0f / (den + 1.0e-6f), aux[gi].y);
+#pragma unroll
+    for (int p = 0; p < PREP_PER; p++) {
+        const int yi = y0 + 8 * p;
+        if (yi >= dim.aheight) break;
+        float den = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 7; i++) den += d[p][i] * k.c[i];
+        side[yi * dim.astride + xi] = make_float2(1.0f / (den + 1.0e-6f), cp[p]);
+    }
 }
 
 // RADIUS > 0: compile-time radius (the loop unrolls); RADIUS == 0: run-time radius.
@@ -1071,10 +1102,11 @@ int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4, int pat
     float2 *aux = cb_ptr<float2>(scratch4);
     float2 *side = aux + (size_t)nbins(dim);
     coefs7 k = load_coefs(coefs);
-    k_bilat_prep1<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+    const dim3 pgrid(dim->astride / 32, (dim->aheight + 8 * PREP_PER - 1) / (8 * PREP_PER));
+    k_bilat_prep1<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(
         aux, cb_ptr<const float4>(src4), pattern, k, dpow, *dim);
     CB_LAUNCH_CHECK();
-    k_bilat_prep2<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
+    k_bilat_prep2<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
     CB_LAUNCH_CHECK();
     const int step = radius == 15 ? bilat_window_step(pattern) : 0;
     if (step) {

@@ -92,6 +92,7 @@ class NativeComm(object):
         self.rank = env_rank if rank is None else rank
         self.world = env_world if world is None else world
         N.ensure_init()
+        N.preload_nccl()
         ident = (ctypes.c_uint8 * 128)()
         if self.rank == 0:
             N.check(N.lib().cb_comm_unique_id(ident))

@@ -132,8 +132,12 @@ def test_c_abi_band_rows_match_the_host_mirror(built):
     assert L.cb_hist_reduce(None, 16, N.byref(dim), 0, None) == N.CB_ERR_INVALID
     assert L.cb_band_gather(None, 16, N.byref(dim), 0, None) == N.CB_ERR_INVALID
     ver = ctypes.c_int()
+    bundled = N.preload_nccl()             # PyTorch's NCCL first, so torch can still load
     if L.cb_comm_version(ctypes.byref(ver)) == 0:       # NCCL present on this box
         assert ver.value >= 21800
+    if bundled:
+        import torch                                    # noqa: F401  (must still import)
+        assert torch.cuda.nccl.version() >= (2, 18)
 
 
 @pytest.mark.gpu
