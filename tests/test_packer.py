@@ -117,3 +117,32 @@ def test_var_args_cover_device_signatures():
         if has_rng:
             rest = rest[1:]
         assert len(rest) == len(varlib.var_args(name)), name
+
+
+def test_pack_constant_row_fast_path_equals_normalize():
+    """Constant rows are written in one vectorised store; the result must be the same
+    bits as normalising every row on its own (interp.py:207-232)."""
+    from cuburn_b200 import samples
+    from cuburn_b200.code import itergen, packer as P
+    from cuburn_b200.genome.use import SplineEval
+    for gnm in (samples.g3(), samples.g6f(), samples.g6f(animated=True), samples.g24h()):
+        pk = itergen.GenomePacker(gnm)
+        times, knots = pk.pack(gnm)
+        want_t = np.full_like(times, 1e9)
+        want_k = np.zeros_like(knots)
+        scale = gnm.get('time', {}).get('duration', 1)
+        nconst = 0
+        for idx, path in enumerate(pk.row_paths):
+            attr = gnm
+            for name in path:
+                if not isinstance(attr, dict) or name not in attr:
+                    attr = P.resolve_spec(pk.spec, path).default
+                    break
+                attr = attr[name]
+            nconst += type(attr) in (int, float)
+            kn = SplineEval.normalize(attr, scale)
+            want_t[idx, :kn.shape[1]] = kn[0]
+            want_k[idx, :kn.shape[1]] = kn[1]
+        assert nconst > 0
+        assert np.array_equal(times.view(np.uint32), want_t.view(np.uint32))
+        assert np.array_equal(knots.view(np.uint32), want_k.view(np.uint32))
