@@ -337,6 +337,34 @@ def test_video_outputs_stream_rendered_frames(native, built, tmp_path):
         assert np.frombuffer(data, 'u1').std() > 1       # an image, not a constant
 
 
+def test_job_farm_renders_frames_through_local_workers(native, built, tmp_path):
+    """distribute.py end to end: the dispatcher starts a worker process per job on this
+    GPU, each renders its frame and streams the JPEG back; a second run resumes (nothing
+    left to do)."""
+    import os
+    import subprocess
+    import sys
+    from PIL import Image
+    from cuburn_b200 import samples
+    from cuburn_b200.genome.util import json_encode
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    flame = tmp_path / 'whirl.json'
+    flame.write_text(json_encode(samples.g6f(animated=True)))
+    cmd = [sys.executable, os.path.join(root, 'distribute.py'), 'dispatch', str(flame),
+           '--worker', 'localhost/0', 'localhost/0', '-P', 'preview', '--spp', '60',
+           '--duration', '1', '--fps', '4', '--skip', '0', '-o', str(tmp_path)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    frames = sorted(tmp_path.glob('whirl_*.jpg'))
+    assert [f.name for f in frames] == ['whirl_%05d.jpg' % i for i in (1, 2, 3, 4)]
+    imgs = [np.array(Image.open(f)).astype(int) for f in frames]
+    assert all(im.shape == (360, 640, 3) and im.max() > 100 for im in imgs)
+    assert np.abs(imgs[0] - imgs[2]).mean() > 0.05              # the flame moves
+    assert not list(tmp_path.glob('*.tmp')) and 'whirl_00003' in r.stderr
+    r2 = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r2.returncode == 0 and 'whirl_0000' not in r2.stderr
+
+
 def test_frame_seed_makes_frames_order_independent(native, built):
     """T11 (animation): with per-frame seeds a frame does not depend on what was rendered
     before it, so frames dealt round-robin to different GPUs equal a sequential render
