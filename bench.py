@@ -181,6 +181,38 @@ def cpu_chaos_rate(nsamples, nthreads=0, seed=1):
     return nsamples / (time.perf_counter() - t), cores
 
 
+def cpu_filter_rates(w=320, h=180):
+    """The numpy restatement of the default filter chain on a small synthetic histogram:
+    algorithmic GB/s per filter (SURVEY 8(d) byte counts), one host core."""
+    from cuburn_b200 import _native as N
+    from oracle import filters_ref as F
+    dim = N.calc_dim(w, h)
+    rs = np.random.RandomState(5)
+    dens = rs.gamma(0.3, 40.0, size=(dim.ah, dim.astride)).astype(np.float32)
+    dens[rs.rand(dim.ah, dim.astride) < 0.3] = 0
+    hist = np.empty((dim.ah, dim.astride, 4), np.float32)
+    for ch in range(3):
+        hist[..., ch] = dens * rs.rand(dim.ah, dim.astride).astype(np.float32)
+    hist[..., 3] = dens
+    nbins = dim.ah * dim.astride
+    k1, k2 = F.logscale_consts(4, 0.5, w, h, 256)
+    stages = (('yuv_to_rgb', 32, lambda p: F.yuv_to_rgb(p)),
+              ('bilateral (8 directions)', 512, lambda p: F.bilateral(p, 1920)),
+              ('logscale', 32, lambda p: F.logscale(p, k1, k2)),
+              ('smearclip', 208, lambda p: F.smearclip(p, 0.7, 4, 0.01)))
+    out, pix, total = {}, hist, 0.0
+    for name, bytes_per_bin, fn in stages:
+        t = time.perf_counter()
+        pix = fn(pix)
+        dt = time.perf_counter() - t
+        total += dt
+        out[name] = bytes_per_bin * nbins / dt / 1e9
+    out['chain'] = 784.0 * nbins / total / 1e9
+    return {'unit': 'GB/s (algorithmic bytes)', 'cores': 1, 'kind': 'port', 'value': out,
+            'sample': 'default chain without output conversion on a %dx%d synthetic histogram '
+                      '(%d bins)' % (w, h, nbins)}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement, all host cores, bounded sample per step."""
     rank = int(os.environ.get('RANK', 0))
@@ -397,6 +429,8 @@ def main():
                'sample': '%d samples (500 spp worth of a 1080p frame) of the same genome, chaos game only'
                          % n_cpu}
 
+    cpu_filters = cpu_filter_rates() if cpu is not None else None
+
     # 3 interp + fill + iter + unswizzle + yuv + 8 x 3 bilateral + logscale + 6 smearclip + convert
     launches_per_step = 3 + 1 + 1 + 1 + 1 + 8 * 3 + 1 + 6 + 1
     line = {
@@ -419,7 +453,7 @@ def main():
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_my / args.steps},
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline, 'roofline_filters': roofline_filters,
-        'cpu_baseline': cpu,
+        'cpu_baseline': cpu, 'cpu_baseline_filters': cpu_filters,
         'wall_s_timed_region': wall,
     }
     if reducer is not None:

@@ -9,6 +9,19 @@ N.init(0)
 cases = [('G6F', 1920, 1080, 2000), ('G3', 1920, 1080, 2000), ('G24H', 1920, 1080, 500)]
 if os.environ.get('CASES'):
     cases = [c for c in cases if c[0] in os.environ['CASES'].split(',')]
+def _medium(nxf, keep_final):
+    """G6F cut down to its first `nxf` xforms (for tuning the heavy / light boundary)."""
+    def make():
+        g = samples.g6f()
+        g['xforms'] = dict((k, v) for k, v in g['xforms'].items() if int(k) < nxf)
+        if not keep_final:
+            g.pop('final_xform', None)
+        return g
+    return make
+samples.GENOMES.update(G4M=_medium(4, False), G3F=_medium(3, True), G2M=_medium(2, False))
+cases += [('G4M', 1920, 1080, 2000), ('G3F', 1920, 1080, 2000), ('G2M', 1920, 1080, 2000)]
+if os.environ.get('CASES'):
+    cases = [c for c in cases if c[0] in os.environ['CASES'].split(',')]
 variants = sys.argv[1:] or ['']
 rmgr = render.RenderManager(seed=1); rmgr.swizzle = {'1': True, '0': False}.get(os.environ.get('SWZ', 'auto'), 'auto')
 for gname, w, h, spp in cases:
