@@ -9,7 +9,6 @@
 
 static thread_local char g_err[16384] = "";
 static int g_sm_count = 148;
-static int g_device = -1;
 
 void cb_set_error(const char *fmt, ...) {
     va_list ap;
@@ -60,7 +59,6 @@ int cb_init(int device) {
         return CB_ERR_INVALID;
     }
     g_sm_count = sms;
-    g_device = device;
     return CB_OK;
 }
 
