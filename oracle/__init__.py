@@ -12,7 +12,7 @@ it can, and the oracle is pinned against every one of them:
   * the reference's own DEVICE code compiled for the CPU from the sources in place
     (oracle/build_ref.py -> oracle/_ref/): all 95 variation bodies, catmull_rom /
     catmull_rom_mag with the knot search, the camera / affine / variation precalc
-    hunks, the YUV helpers, interp_palette_flat, every filter kernel (run through a
+    hunks, precalc_densities (3 and 6 xforms), the YUV helpers, interp_palette_flat, every filter kernel (run through a
     serial CUDA shim with clamp-to-edge textures) and all six f32_to_* pixel-format
     kernels -- tests/test_reference_code.py
   * the reference's own HOST code executed under Python 3 (tests/golden/make_*_golden.py):
@@ -23,7 +23,7 @@ it can, and the oracle is pinned against every one of them:
 
 Not covered by reference-generated vectors: the `iter` kernel's own control flow
 (weighted xform choice, inter-warp shuffle, binning through `cvt.rni`, packed-u64
-accumulation and `flush_atom` -- tempita control flow plus inline PTX) and
-`precalc_densities`.  For those the oracle is a line-by-line restatement of the cited
-sources: **parity unpinned** for that part only.
+accumulation and `flush_atom` -- nested tempita control flow plus inline PTX).  There
+the oracle is a line-by-line restatement of the cited sources: **parity unpinned** for
+that part only.
 """

@@ -36,7 +36,11 @@ def available():
 
 class _Template(object):
     """Stand-in for tempita.Template: keeps the raw text; renders ``{{expr}}``
-    placeholders (no control flow) by evaluating them against the arguments."""
+    placeholders by evaluating them against the arguments, and un-nested
+    ``{{for x in expr}} ... {{endfor}}`` loops (what precalc_densities needs); any
+    other control flow is refused."""
+    _LOOP = re.compile(r'\{\{for (\w+) in (.*?)\}\}(.*?)\{\{endfor\}\}', re.S)
+
     def __init__(self, content, name=None, namespace=None, **kw):
         self.content, self.name, self.namespace = content, name, namespace or {}
 
@@ -46,9 +50,20 @@ class _Template(object):
             if isinstance(d, dict):
                 ns.update(d)
         ns.update(kw)
-        if '{{for' in self.content or '{{if' in self.content or '{{py:' in self.content:
+
+        def fill(text, scope):
+            return re.sub(r'\{\{(.*?)\}\}', lambda m: str(eval(m.group(1), scope)), text)
+
+        def loop(m):
+            var, expr, body = m.groups()
+            if '{{for' in body:
+                raise RuntimeError('template %s nests loops' % self.name)
+            return ''.join(fill(body, dict(ns, **{var: item})) for item in eval(expr, ns))
+
+        text = self._LOOP.sub(loop, self.content)
+        if '{{for' in text or '{{if' in text or '{{py:' in text:
             raise RuntimeError('template %s uses control flow' % self.name)
-        return re.sub(r'\{\{(.*?)\}\}', lambda m: str(eval(m.group(1), ns)), self.content)
+        return fill(text, ns)
 
 
 class _FakeNode(object):
@@ -82,6 +97,22 @@ class _FakeNode(object):
         if ident not in self._reg['in']:
             self._reg['in'].append(ident)
         return ident
+
+
+class _FakeXforms(object):
+    """``cp.xforms`` of the packer view for a genome with xforms named `names`, in
+    the reference's iteration order: a Python 2 dict-like whose ``keys()`` slices."""
+    def __init__(self, node, names):
+        self._node, self._names = node, list(names)
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def keys(self):
+        return list(self._names)
+
+    def __getitem__(self, name):
+        return getattr(self._node, name)
 
 
 def _precalc_function(cname, codes, reg, extra_args=''):
@@ -350,6 +381,14 @@ extern "C" void ref_catmull_rom(const float *times, const float *knots, const fl
     itermod.precalc_xf_affine(px)
     parts.append(_precalc_function('ref_precalc_affine', px._codes, px._reg))
     meta['precalc']['affine'] = px._reg
+    # cumulative xform densities (code/iter.py:12-30) for 3- and 6-xform genomes
+    for names in (('0', '1', '2'), ('0', '1', '2', '3', '4', '5')):
+        cp = _FakeNode('cp')
+        cp.__dict__['xforms'] = _FakeXforms(_FakeNode('xf', cp._reg, cp._codes), names)
+        itermod.precalc_densities(cp)
+        kind = 'densities%d' % len(names)
+        parts.append(_precalc_function('ref_precalc_' + kind, cp._codes, cp._reg))
+        meta['precalc'][kind] = cp._reg
     for vname in ('waves', 'perspective', 'julian', 'juliascope', 'curve'):
         reg, codes = {'in': [], 'out': []}, []
         pvn, pxn = _FakeNode('pv', reg, codes), _FakeNode('px', reg, codes)

@@ -174,6 +174,32 @@ def test_device_variation_vs_reference_code(native, built, name):
     assert badfrac <= (0.02 if name in _DISCONTINUOUS else 0.0), (name, badfrac, float(err[ok].max()))
 
 
+# ---- cumulative xform densities (code/iter.py:12-30) -----------------------------------
+def test_precalc_densities_equal_reference_code(built):
+    """The reference's precalc_densities template, rendered for 3 and 6 xforms and
+    compiled for the CPU, against the oracle's restatement: the same float32
+    operations in the same order, so the cumulative densities agree bit for bit."""
+    B = _ref()
+    from oracle import flame_ref as R
+    from cuburn_b200 import samples
+    rs = np.random.RandomState(11)
+    for make, kind in ((samples.g3, 'densities3'), (samples.g6f, 'densities6')):
+        for trial in range(40):
+            g = make()
+            names = sorted(g['xforms'])
+            weights = rs.uniform(0.01, 5.0, len(names)) * rs.choice([1.0, 1e-3, 30.0], len(names))
+            for n, wgt in zip(names, weights):
+                g['xforms'][n]['weight'] = float(wgt)
+            ev = R.GenomeEval(g, 640, 360, 0.5, 0.0)
+            want = B.ref_precalc(kind, dict(('in_xf_%s_weight' % n, np.float32(wgt))
+                                            for n, wgt in zip(names, weights)))
+            assert sorted(want) == ['out_cp_den_%s' % n for n in names[:-1]]
+            for n in names[:-1]:
+                got = np.float32(ev.values['xforms.%s.density' % n][0])
+                assert got.view(np.uint32) == np.float32(want['out_cp_den_%s' % n]).view(np.uint32), \
+                    (kind, trial, n, got, want)
+
+
 # ---- precalc hunks (code/iter.py:56-95, variation precalcs) ----------------------------
 def test_precalc_equals_reference_code(built):
     B = _ref()
