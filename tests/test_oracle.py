@@ -196,3 +196,14 @@ def test_chaos_single_thread_is_deterministic(built):
     c, _ = R.iterate(ev, pal, seeds, 200000, ntraj=32, nthreads=4)
     assert np.array_equal(a[..., 3], c[..., 3])           # counts are order independent
     assert np.allclose(a, c, rtol=1e-5, atol=1e-4)
+
+
+def test_bench_cpu_filter_baseline_reports_every_stage():
+    """bench.py's CPU arm for the filter chain (the numpy restatement, timed per filter)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    r = bench.cpu_filter_rates(w=96, h=54)
+    assert set(r['value']) == {'yuv_to_rgb', 'bilateral (8 directions)', 'logscale', 'smearclip',
+                               'chain'}
+    assert all(v > 0 for v in r['value'].values()) and r['cores'] == 1 and r['kind'] == 'port'

@@ -146,3 +146,19 @@ def test_pack_constant_row_fast_path_equals_normalize():
         assert nconst > 0
         assert np.array_equal(times.view(np.uint32), want_t.view(np.uint32))
         assert np.array_equal(knots.view(np.uint32), want_k.view(np.uint32))
+
+
+def test_reduction_placement_follows_the_genome_weight():
+    """itergen.is_heavy picks where the histogram reduction sits relative to the
+    exchange barrier (measured per genome class, profiles/r01_iter_variants.md)."""
+    from cuburn_b200 import samples
+    from cuburn_b200.code import itergen
+    heavy = {name: itergen.is_heavy(itergen.GenomePacker(make()))
+             for name, make in samples.GENOMES.items()}
+    assert heavy == {'G3': False, 'G6F': True, 'G24H': True}
+    for name, make in samples.GENOMES.items():
+        src = itergen.generate_source(itergen.GenomePacker(make()), 1)
+        assert ('#define RED_BEFORE_PULL %d' % heavy[name]) in src
+        forced = itergen.generate_source(itergen.GenomePacker(make()), 1,
+                                         extra_defines={'RED_BEFORE_PULL': 0})
+        assert forced.count('#define RED_BEFORE_PULL') == 1
