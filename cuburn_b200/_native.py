@@ -60,7 +60,7 @@ class IterArgs(ctypes.Structure):
                 ('pal_rows', c_int32), ('fuse_rounds', c_int32), ('swizzle_bins', c_int32),
                 ('first_sample', c_uint64), ('nsamples', c_uint64),
                 ('total_samples', c_uint64), ('cells', c_uint64),
-                ('palette_packed', c_uint64)]
+                ('palette_packed', c_uint64), ('hot_tags', c_uint64)]
 
 
 _SIGNATURES = {
@@ -110,6 +110,8 @@ _SIGNATURES = {
     'cb_palette_pack': (c_int, [c_uint64, c_uint64, c_int, c_void_p]),
     'cb_flush_packed': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_hist_unswizzle': (c_int, [c_uint64, c_uint64, c_int, POINTER(Dims), c_void_p]),
+    'cb_hot_scan': (c_int, [c_uint64, c_uint64, c_uint64, c_uint64, c_int, c_float,
+                            POINTER(Dims), c_void_p]),
     'cb_yuv_to_rgb': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_den_blur': (c_int, [c_uint64, c_uint64, c_int, c_int, POINTER(c_float),
                             POINTER(Dims), c_void_p]),

@@ -36,40 +36,89 @@ def load_headers():
     return list(HEADER_NAMES), out
 
 
-def _affine_lines(packer, apath, src_x, src_y, dst_x, dst_y):
-    s = {c: packer.slot(apath + (c,)) for c in AFFINE_COEFS}
-    return [
-        '    %s = P[%d] * %s + P[%d] * %s + P[%d];' % (dst_x, s['xx'], src_x, s['xy'], src_y, s['xo']),
-        '    %s = P[%d] * %s + P[%d] * %s + P[%d];' % (dst_y, s['yx'], src_x, s['yy'], src_y, s['yo']),
+class _Params(object):
+    """
+    How generated code reads parameter slots.  Stills: ``P[slot]`` with a constant index
+    is a constant-bank operand.  Motion blur: the block lives in shared memory, where
+    every scalar read is an LDS through the pipe the histogram reductions use
+    (profiles/r01_iter_variants.md: +20 % frame time); the slots of an xform are
+    contiguous, so they are fetched as aligned float4s -- a quarter of the loads --
+    declared right before their first use so the compiler sees short live ranges.
+    """
+    def __init__(self, vector):
+        self.vector = vector
+        self.loaded = set()
+
+    def ref(self, slot, lines):
+        if not self.vector:
+            return 'P[%d]' % slot
+        k = slot // 4
+        if k not in self.loaded:
+            self.loaded.add(k)
+            lines.append('    const float4 q%d = P4[%d];' % (k, k))
+        return 'q%d.%s' % (k, 'xyzw'[slot % 4])
+
+
+def _affine_lines(packer, prm, apath, src_x, src_y, dst_x, dst_y):
+    L = []
+    s = {c: prm.ref(packer.slot(apath + (c,)), L) for c in AFFINE_COEFS}
+    return L + [
+        '    %s = %s * %s + %s * %s + %s;' % (dst_x, s['xx'], src_x, s['xy'], src_y, s['xo']),
+        '    %s = %s * %s + %s * %s + %s;' % (dst_y, s['yx'], src_x, s['yy'], src_y, s['yo']),
     ]
 
 
-def _xform_function(packer, fname, xpath, variations, has_post):
+def _xform_function(packer, fname, xpath, variations, has_post, vector=False):
+    prm = _Params(vector)
     L = ['__device__ __forceinline__ void %s(float &x, float &y, '
          'float &color, mwc_st &rng) {' % fname,
          '    float tx, ty;']
-    L += _affine_lines(packer, xpath + ('pre_affine',), 'x', 'y', 'tx', 'ty')
+    L += _affine_lines(packer, prm, xpath + ('pre_affine',), 'x', 'y', 'tx', 'ty')
     L.append('    float ox = 0.0f, oy = 0.0f;')
     # variations in sorted-name order (use.py:90-91, iter.py:132-137)
     for v in variations:
         vpath = xpath + ('variations', v)
-        args = ['tx', 'ty', 'P[%d]' % packer.slot(vpath + ('weight',)), 'ox', 'oy']
+        args = ['tx', 'ty', prm.ref(packer.slot(vpath + ('weight',)), L), 'ox', 'oy']
         if varlib.uses_rng(v):
             args.append('rng')
         for kind, name in varlib.var_args(v):
             if kind == 'pre':
-                args.append('P[%d]' % packer.slot(xpath + ('pre_affine', name)))
+                args.append(prm.ref(packer.slot(xpath + ('pre_affine', name)), L))
             else:
-                args.append('P[%d]' % packer.slot(vpath + (name,)))
+                args.append(prm.ref(packer.slot(vpath + (name,)), L))
         L.append('    var_%s(%s);' % (v, ', '.join(args)))
     if has_post:
         L.append('    tx = ox; ty = oy;')
-        L += _affine_lines(packer, xpath + ('post_affine',), 'tx', 'ty', 'ox', 'oy')
+        L += _affine_lines(packer, prm, xpath + ('post_affine',), 'tx', 'ty', 'ox', 'oy')
     L.append('    x = ox; y = oy;')
-    L.append('    float csp = P[%d];' % packer.slot(xpath + ('color_speed',)))
-    L.append('    color = color * (1.0f - csp) + P[%d] * csp;' % packer.slot(xpath + ('color',)))
+    L.append('    float csp = %s;' % prm.ref(packer.slot(xpath + ('color_speed',)), L))
+    L.append('    color = color * (1.0f - csp) + %s * csp;'
+             % prm.ref(packer.slot(xpath + ('color',)), L))
     L.append('}')
     return '\n'.join(L)
+
+
+def _choice_chain(packer, prm, names, den_slot, indent, xaos):
+    """The cumulative-density if-chain over the xforms (iter.py:263-272; with xaos one
+    chain per previous xform, iter.py:236-257).  ``den_slot(i)`` is the slot of the
+    cumulative density that ends xform i's interval."""
+    L = []
+    refs = [prm.ref(den_slot(i), L) for i in range(len(names) - 1)]
+    for i, (fname, xpath) in enumerate(names):
+        if i < len(names) - 1:
+            head = '%sif (sel <= %s) {' % ('else ' if i else '', refs[i])
+        else:
+            head = 'else {' if len(names) > 1 else '{'
+        body = ' %s(x, y, color, rng);' % fname
+        if xpath in packer.opacity:
+            OL = []
+            op = _Params(prm.vector).ref(packer.opacity[xpath], OL)
+            body += ''.join(' ' + l.strip() for l in OL)
+            body += ' vis = opacity_visible(%s, rng);' % op
+        if xaos:
+            body += ' last = %d;' % i
+        L.append('%s%s%s }' % (indent, head, body))
+    return L
 
 
 def is_heavy(packer):
@@ -83,23 +132,28 @@ def is_heavy(packer):
     return sum(len(variations) for _, variations, _ in packer.xforms) >= 12
 
 
-def generate_source(packer, params_const=False, extra_defines=None, acc_packed=False):
+def generate_source(packer, params_const=False, extra_defines=None, acc_packed=False,
+                    hot_bins=False):
     """
     CUDA source of the iterate module for ``packer``'s genome structure.
     ``params_const`` selects the variant whose parameter block lives in
-    __constant__ memory (one block per launch: stills) instead of shared memory.
+    __constant__ memory (one block per launch: stills) instead of shared memory;
+    ``acc_packed`` the packed-u64 accumulation; ``hot_bins`` the variant that keeps
+    private shared-memory cells for the bins listed in ``iter_args::hot_tags``.
     """
+    extra_defines = dict(extra_defines or {})
+    vector = (not params_const) and extra_defines.pop('PARAMS_VECTOR', '1') != '0'
     out = ['// generated by cuburn_b200.code.itergen -- do not edit']
-    for k, v in (extra_defines or {}).items():
+    for k, v in extra_defines.items():
         out.append('#define %s %s' % (k, v))
     out += ['#include "mwc.cuh"', '#include "variations.cuh"', '']
     out.append('#define NSLOTS %d' % packer.nslots)
     out.append('#define PARAMS_CONST %d' % (1 if params_const else 0))
     out.append('#define ACC_PACKED %d' % (1 if acc_packed else 0))
-    for c in AFFINE_COEFS:
-        out.append('#define CAM_%s %d' % (c.upper(), packer.slot('camera', c)))
+    out.append('#define HOT_BINS %d' % (1 if hot_bins else 0))
+    out.append('#define XAOS %d' % (1 if packer.xaos else 0))
     out.append('#define HAS_FINAL %d' % (1 if packer.has_final else 0))
-    if 'RED_BEFORE_PULL' not in (extra_defines or {}):
+    if 'RED_BEFORE_PULL' not in extra_defines:
         out.append('#define RED_BEFORE_PULL %d' % (1 if is_heavy(packer) else 0))
     out.append('#include "iter_params.cuh"')
     out.append('')
@@ -111,16 +165,28 @@ def generate_source(packer, params_const=False, extra_defines=None, acc_packed=F
         else:
             fname = 'apply_xf_%d' % len(names)
             names.append((fname, xpath))
-        out.append(_xform_function(packer, fname, xpath, variations, has_post))
+        out.append(_xform_function(packer, fname, xpath, variations, has_post, vector))
         out.append('')
 
-    L = ['__device__ __forceinline__ void chaos_step(float sel, '
-         'float &x, float &y, float &color, mwc_st &rng) {']
-    for i, (fname, xpath) in enumerate(names[:-1]):
-        L.append('    %sif (sel <= P[%d]) %s(x, y, color, rng);'
-                 % ('else ' if i else '', packer.slot(xpath + ('density',)), fname))
-    last = names[-1][0]
-    L.append('    %s%s(x, y, color, rng);' % ('else ' if len(names) > 1 else '', last))
+    L = ['__device__ __forceinline__ bool chaos_step(float sel, float &x, float &y, '
+         'float &color, int &last, mwc_st &rng) {',
+         '    bool vis = true;']
+    ids = [xpath[1] for _, xpath in names]
+    if packer.xaos:
+        L.append('    switch (last) {')
+        for p, pid in enumerate(ids):
+            prm = _Params(vector)
+            L.append('    %s: {' % ('default' if p == len(ids) - 1 else 'case %d' % p))
+            L += _choice_chain(packer, prm, names,
+                               lambda i: packer.slot(('xforms', pid, 'chaos_den', ids[i])),
+                               '        ', True)
+            L.append('        break; }')
+        L.append('    }')
+    else:
+        prm = _Params(vector)
+        L += _choice_chain(packer, prm, names,
+                           lambda i: packer.slot(('xforms', ids[i], 'density')), '    ', False)
+    L.append('    return vis;')
     L.append('}')
     out.append('\n'.join(L))
     out.append('')
@@ -129,11 +195,18 @@ def generate_source(packer, params_const=False, extra_defines=None, acc_packed=F
                    'float &y, float &color, mwc_st &rng) {\n'
                    '    apply_xf_final(x, y, color, rng);\n}')
         out.append('')
+    # camera affine (iter.py:302-311) as six named coefficients
+    prm, CL = _Params(vector), []
+    cam = [prm.ref(packer.slot('camera', c), CL) for c in AFFINE_COEFS]
+    out.append('__device__ __forceinline__ void camera_coefs(float &xx, float &xy, float &xo, '
+               'float &yx, float &yy, float &yo) {\n%s    xx = %s; xy = %s; xo = %s; yx = %s; '
+               'yy = %s; yo = %s;\n}\n' % (''.join(l + '\n' for l in CL), *cam))
     out.append('#include "iter_kernel.cuh"')
     return '\n'.join(out) + '\n'
 
 
-def mkiterlib(gnm, params_const=False, acc_packed=False):
+def mkiterlib(gnm, params_const=False, acc_packed=False, hot_bins=False):
     """``(packer, source)`` for a genome (mirrors iter.mkiterlib, iter.py:559-575)."""
     packer = GenomePacker(gnm)
-    return packer, generate_source(packer, params_const, acc_packed=acc_packed)
+    return packer, generate_source(packer, params_const, acc_packed=acc_packed,
+                                   hot_bins=hot_bins)

@@ -24,7 +24,7 @@ from ..genome.use import SplineEval
 from ..genome.util import resolve_spec
 from ..genome.variations import var_param_order
 from . import varlib
-from .varlib import (OP_DIRECT, OP_DIRECT_MAG, OP_AFFINE, OP_CAMERA, OP_DENSITY)
+from .varlib import (OP_DIRECT, OP_DIRECT_MAG, OP_AFFINE, OP_CAMERA, OP_DENSITY, OP_XAOS)
 
 SEARCH_ROUNDS = 5
 MAX_KNOTS = 1 << SEARCH_ROUNDS
@@ -52,6 +52,11 @@ class GenomePacker(object):
         self.has_final = 'final_xform' in gnm
         # (xform path, variation names in sorted order, has post affine)
         self.xforms = []
+        # xform path -> slot of its opacity, for xforms that carry one (specs.py:17)
+        self.opacity = {}
+        # xaos: the choice of the next xform depends on the previous one
+        # (precalc_chaos, iter.py:32-54); used when any xform has a 'chaos' map
+        self.xaos = any('chaos' in gnm['xforms'][xid] for xid in self.xform_ids)
 
         # weights first so the density op sees one contiguous block of rows
         wrows = [self._row(('xforms', xid, 'weight')) for xid in self.xform_ids]
@@ -62,12 +67,19 @@ class GenomePacker(object):
         if self.has_final:
             self._add_xform(('final_xform',), gnm['final_xform'])
 
-        if len(self.xform_ids) > 1:
+        if len(self.xform_ids) > 1 and not self.xaos:
             first = None
             for xid in self.xform_ids[:-1]:
                 s = self._slot(('xforms', xid, 'density'))
                 first = s if first is None else first
             self._op(OP_DENSITY, first, [wrows[0]], aux0=len(self.xform_ids))
+        if len(self.xform_ids) > 1 and self.xaos:
+            # per previous xform p: cumulative normalised weight[n] * chaos[p][n]
+            for pid in self.xform_ids:
+                crows = [self._row(('xforms', pid, 'chaos', nid)) for nid in self.xform_ids]
+                assert crows == list(range(crows[0], crows[0] + len(crows)))
+                first = self._slot_block(('xforms', pid, 'chaos_den'), self.xform_ids[:-1])
+                self._op(OP_XAOS, first, [wrows[0], crows[0]], aux0=len(self.xform_ids))
 
         cam_rows = [self._row(('camera', 'rotation')),
                     self._row(('camera', 'center', 'x')),
@@ -95,6 +107,9 @@ class GenomePacker(object):
             self._affine(xpath + ('post_affine',))
         self._direct(xpath + ('color',))
         self._direct(xpath + ('color_speed',))
+        if 'opacity' in xf:
+            self._direct(xpath + ('opacity',))
+            self.opacity[xpath] = self.slot(xpath + ('opacity',))
         for v in variations:
             vpath = xpath + ('variations', v)
             self._direct(vpath + ('weight',))
@@ -182,6 +197,9 @@ class GenomePacker(object):
         for idx, path in enumerate(self.row_paths):
             attr = gnm
             for name in path:
+                if isinstance(attr, dict) and name not in attr and name.isdigit() \
+                        and int(name) in attr:
+                    name = int(name)        # chaos maps straight from the converter
                 if not isinstance(attr, dict) or name not in attr:
                     attr = resolve_spec(self.spec, path).default
                     break

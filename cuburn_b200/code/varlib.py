@@ -22,7 +22,7 @@ RNG_USERS = frozenset("""julia noise julian juliascope blur gaussian_blur
 
 # precalc op codes shared with the device interpreter
 OP_DIRECT, OP_DIRECT_MAG, OP_AFFINE, OP_CAMERA, OP_DENSITY = 0, 1, 2, 3, 4
-OP_WAVES, OP_PERSPECTIVE, OP_JULIAN_CN, OP_CURVE = 5, 6, 7, 8
+OP_WAVES, OP_PERSPECTIVE, OP_JULIAN_CN, OP_CURVE, OP_XAOS = 5, 6, 7, 8, 9
 
 # name -> (op, inputs, outputs); inputs starting with '^' are relative to the
 # xform (not the variation).

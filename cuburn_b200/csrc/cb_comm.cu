@@ -9,7 +9,20 @@
 #include <stdlib.h>
 #include <string.h>
 
+// NCCL is bound with dlopen at run time, so its header is not needed to build: when the
+// development package is absent the handful of ABI types used here (stable since NCCL 2.0)
+// are declared locally.
+#if defined(__has_include) && __has_include(<nccl.h>)
 #include <nccl.h>
+#else
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+typedef enum { ncclFloat32 = 7, ncclFloat = 7 } ncclDataType_t;
+}
+#endif
 
 #include "cb_common.h"
 

@@ -270,6 +270,41 @@ struct op_colorclip : op_base {
     }
 };
 
+// ---- hot-bin scan (iterate support) -------------------------------------------------
+// After a short pilot pass of the chaos game, find the bins that hold at least
+// `threshold` samples and enter them into the direct-mapped table the HOT_BINS variant
+// of the iterate kernel keeps in shared memory (device/iter_kernel.cuh).  Where two hot
+// bins hash to one slot the hotter one wins (atomicMax on density << 32 | bin); the
+// other stays on the global-reduction path.  The reference's counterpart is the hotspot
+// flag computation at the end of flush_atom (code/iter.py:481-526).
+#define HOT_SLOTS 512
+#define HOT_HASH_MUL 2654435761u
+#define HOT_HASH_SHIFT 23
+#define HIST_SWZ_INV 30599u          // 40503 * 30599 = 1 (mod 65536)
+
+__global__ void __launch_bounds__(256)
+k_hot_scan(unsigned long long *best, const float4 *hist, int nbins, int swizzle_bins,
+           float threshold) {
+    const int i = blockIdx.x * 256 + threadIdx.x;      // storage index
+    if (i >= nbins) return;
+    const float w = hist[i].w;
+    if (w < threshold) return;
+    unsigned int u = (unsigned int)i;
+    if (i < swizzle_bins) u = (u & 0xffff0000u) | ((u * HIST_SWZ_INV) & 0xffffu);
+    const unsigned int slot = (u * HOT_HASH_MUL) >> HOT_HASH_SHIFT;
+    atomicMax(best + slot, ((unsigned long long)__float_as_uint(w) << 32) | u);
+}
+
+__global__ void __launch_bounds__(HOT_SLOTS)
+k_hot_finish(int *tags, int *count, unsigned long long *best) {
+    const int s = threadIdx.x;
+    const unsigned long long b = best[s];
+    tags[s] = b ? (int)(unsigned int)b : -1;
+    best[s] = 0ull;                                    // ready for the next frame
+    const int n = __syncthreads_count(b != 0ull);
+    if (s == 0) *count = n;
+}
+
 // ---- 7-tap directional blurs ----------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_den_blur(float *dst, const float4 *src, int pattern, int upsample, coefs7 k,
@@ -950,6 +985,22 @@ int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream 
     k_map4x2<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(
         cb_ptr<float4>(hist4), cb_ptr<const float4>(hist4),
         cb_ptr<const unsigned long long>(cells), nbins(dim), op_flush_packed());
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
+                int swizzle_bins, float threshold, const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(swizzle_bins >= 0 && swizzle_bins % 65536 == 0 && swizzle_bins <= nbins(dim),
+               "swizzle_bins must be a multiple of 65536 inside the grid");
+    CB_REQUIRE(threshold >= 1.0f, "threshold below one sample");
+    k_hot_scan<<<(nbins(dim) + 255) / 256, 256, 0, cb_cs(s)>>>(
+        cb_ptr<unsigned long long>(scratch), cb_ptr<const float4>(hist4), nbins(dim),
+        swizzle_bins, threshold);
+    CB_LAUNCH_CHECK();
+    k_hot_finish<<<1, HOT_SLOTS, 0, cb_cs(s)>>>(cb_ptr<int>(tags), cb_ptr<int>(count),
+                                                cb_ptr<unsigned long long>(scratch));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -96,7 +96,7 @@ k_interp_rows(float *vals, const float *times, const float *knots,
 // Program word layout: {op, out_slot, in[0..7], aux0, aux1}
 #define PROG_W 12
 enum { OP_DIRECT = 0, OP_DIRECT_MAG, OP_AFFINE, OP_CAMERA, OP_DENSITY,
-       OP_WAVES, OP_PERSPECTIVE, OP_JULIAN_CN, OP_CURVE };
+       OP_WAVES, OP_PERSPECTIVE, OP_JULIAN_CN, OP_CURVE, OP_XAOS };
 
 #define DEG2RAD(a) FD(FM((a), 3.14159274101257f), 180.0f)
 
@@ -159,6 +159,21 @@ k_interp_params(float *params, int stride, const float *vals, int nrows,
             sum = 0.0f;
             for (int k = 0; k < n - 1; k++) {
                 sum = FA(sum, FM(v[in[0] + k], rsum));
+                out[dst + k] = sum;
+            }
+            break;
+        }
+        case OP_XAOS: {
+            // in[0] = first weight row, in[1] = first row of the previous xform's chaos
+            // multipliers, aux0 = xform count; writes count-1 cumulative normalised
+            // weight * chaos products (precalc_chaos, iter.py:32-54)
+            int n = w[10];
+            float sum = 0.0f;
+            for (int k = 0; k < n; k++) sum = FA(sum, FM(v[in[0] + k], v[in[1] + k]));
+            float rsum = FD(1.0f, sum);
+            sum = 0.0f;
+            for (int k = 0; k < n - 1; k++) {
+                sum = FA(sum, FM(FM(v[in[0] + k], v[in[1] + k]), rsum));
                 out[dst + k] = sum;
             }
             break;

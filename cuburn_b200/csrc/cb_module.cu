@@ -26,6 +26,7 @@ struct DriverApi {
                              unsigned, unsigned, unsigned, CUstream, void **,
                              void **) = nullptr;
     CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int,
                                                           size_t) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
@@ -57,6 +58,7 @@ int ensure_driver() {
         !load_entry("cuModuleGetFunction", &g_drv.ModuleGetFunction) ||
         !load_entry("cuLaunchKernel", &g_drv.LaunchKernel) ||
         !load_entry("cuFuncGetAttribute", &g_drv.FuncGetAttribute) ||
+        !load_entry("cuFuncSetAttribute", &g_drv.FuncSetAttribute) ||
         !load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor",
                     &g_drv.OccupancyMaxActiveBlocksPerMultiprocessor) ||
         !load_entry("cuGetErrorString", &g_drv.GetErrorString) ||
@@ -189,6 +191,10 @@ int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,
     CUfunction f;
     int rc = module_function(m, kernel, &f);
     if (rc != CB_OK) return rc;
+    CB_REQUIRE(dyn_smem >= 0 && dyn_smem <= 227 * 1024, "dynamic shared memory beyond 227 KB");
+    if (dyn_smem > 48 * 1024)       // opt in to the large carve-out (up to 227 KB per CTA)
+        CB_DRV(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                      dyn_smem));
     CB_DRV(g_drv.LaunchKernel(f, gx, gy, gz, bx, by, bz, dyn_smem,
                               (CUstream)cb_cs(s), args, nullptr));
     return CB_OK;

@@ -2,16 +2,25 @@
 //
 // Included at the end of a generated translation unit that defines
 //   NSLOTS                number of packed parameter floats per temporal sample
-//   CAM_XX .. CAM_YO      slot indices of the camera affine
+//   void camera_coefs(float &xx, ..., float &yo)   the camera affine's coefficients
 //   HAS_FINAL             0/1
 //   PARAMS_CONST          1: one parameter block for the whole launch, read from
 //                            __constant__ memory (stills: every temporal sample is
 //                            identical); parameters become constant-bank operands
 //                         0: the block of the unit's temporal sample is staged in
 //                            shared memory (motion blur)
-//   void chaos_step(float sel, float &x, float &y, float &c, mwc_st &rng)
-//                         the weighted xform choice + application; reads P[slot]
+//   bool chaos_step(float sel, float &x, float &y, float &c, int &last, mwc_st &rng)
+//                         the weighted xform choice + application; reads P[slot];
+//                         returns whether the new point is visible (xform opacity,
+//                         genome/specs.py:17); `last` is the index of the xform the
+//                         point went through before (only read when XAOS) and is
+//                         updated
 //   void final_step(float &x, float &y, float &c, mwc_st &rng)   (if HAS_FINAL)
+//   XAOS                  0/1: xform choice depends on the previous xform of the
+//                         trajectory (iter.py:32-54,233-257); as in the reference the
+//                         choice is then per thread and points are not exchanged
+//   HOT_BINS              0/1: samples for the bins listed in iter_args::hot_tags are
+//                         accumulated in shared memory (see below)
 // and which #includes "iter_params.cuh" *before* those functions so that P exists.
 //
 // What it computes is the reference `iter` kernel (cuburn/code/iter.py:157-418):
@@ -50,12 +59,26 @@ struct iter_args {
     unsigned long long nsamples;
     unsigned long long total_samples;
     unsigned long long *cells;                 // ACC_PACKED: u64 [aheight][astride]
-    const unsigned long long *palette_packed;  // ACC_PACKED: u64 [pal_rows][256]
+    const unsigned long long *palette_packed;  // ACC_PACKED / HOT_BINS: u64 [pal_rows][256]
+    const int *hot_tags;                       // HOT_BINS: int [HOT_SLOTS], bin or -1
 };
 
 #ifndef ACC_PACKED
 #define ACC_PACKED 0
 #endif
+#ifndef XAOS
+#define XAOS 0
+#endif
+#ifndef HOT_BINS
+#define HOT_BINS 0
+#endif
+// Slots of the per-CTA hot-bin table: a direct-mapped hash of the bin index.
+#define HOT_SLOTS 512
+#define HOT_HASH_MUL 2654435761u
+#define HOT_HASH_SHIFT 23
+// Units between two flushes of the table into the histogram: keeps the 32-bit level
+// sums of a cell (<= 255 x samples) and the float conversion of its count exact.
+#define HOT_FLUSH_UNITS 32
 
 #define ITER_WARPS (ITER_THREADS / 32)
 #define UNIT_SAMPLES (ITER_THREADS * UNIT_ROUNDS)
@@ -108,8 +131,10 @@ __device__ __forceinline__ void reseed_point(float &x, float &y, float &c, mwc_s
 // code/util.py:194-200).  The unsigned compare also rejects negative
 // coordinates; the x bound is astride, not awidth, as in the reference.
 __device__ __forceinline__ int sample_bin(float x, float y, int astride, int aheight) {
-    float cx = __fmaf_rn(P[CAM_XX], x, __fmaf_rn(P[CAM_XY], y, P[CAM_XO]));
-    float cy = __fmaf_rn(P[CAM_YX], x, __fmaf_rn(P[CAM_YY], y, P[CAM_YO]));
+    float xx, xy, xo, yx, yy, yo;
+    camera_coefs(xx, xy, xo, yx, yy, yo);
+    float cx = __fmaf_rn(xx, x, __fmaf_rn(xy, y, xo));
+    float cy = __fmaf_rn(yx, x, __fmaf_rn(yy, y, yo));
     unsigned int ix = (unsigned int)__float2int_rn(cx);
     unsigned int iy = (unsigned int)__float2int_rn(cy);
     if (ix >= (unsigned int)astride || iy >= (unsigned int)aheight) return -1;
@@ -159,6 +184,44 @@ __device__ __forceinline__ int exchange_slot(int tid, int warp, int lane, int ro
 #endif
 }
 
+// ---- hot bins ----------------------------------------------------------------------
+// One histogram address absorbs ~6.5e8 reductions/s (profiles/r01_red_microbench.json),
+// so a flame that sends more than ~0.4 % of its samples to one bin is bound by that
+// bin, not by the GPU.  The reference thins such bins (1 sample in 2 / 8 / 32 with a
+// 2 / 8 / 32-fold weight, iter.py:319-329 with the flags of iter.py:442-526); here the
+// bins a short pilot pass found hot (cb_hot_scan) get a private cell in the CTA's
+// shared memory -- sm_100a retires 7e11 shared 2 x ATOMS.ADD/s against 1.9e11 L2
+// reductions (profiles/r02_smem_atomics.md) -- holding integer level sums, and each
+// CTA folds its cells into the histogram every HOT_FLUSH_UNITS units.  Exact where the
+// float4 path rounds: a hot bin's colour sums are integers until the flush.
+#if HOT_BINS
+#if ACC_PACKED
+#error "HOT_BINS is an option of the float4 accumulation"
+#endif
+struct hot_table {
+    int tag[HOT_SLOTS];                     // bin index owning the slot, -1 = none
+    unsigned int cell[HOT_SLOTS][4];        // count, sum Y, sum U, sum V of 8-bit levels
+};
+
+__device__ __forceinline__ unsigned int hot_slot(int bin) {
+    return ((unsigned int)bin * HOT_HASH_MUL) >> HOT_HASH_SHIFT;
+}
+
+// Called by the whole CTA between two barriers.
+__device__ __forceinline__ void hot_flush(hot_table *ht, const iter_args &a, int tid) {
+    for (int s = tid; s < HOT_SLOTS; s += ITER_THREADS) {
+        const unsigned int n = ht->cell[s][0];
+        if (n) {
+            const float k = 1.0f / 255.0f;
+            red_add_f32x4(a.hist + swizzle_bin(ht->tag[s], a.swizzle_bins),
+                          make_float4((float)ht->cell[s][1] * k, (float)ht->cell[s][2] * k,
+                                      (float)ht->cell[s][3] * k, (float)n));
+            ht->cell[s][0] = 0u; ht->cell[s][1] = 0u; ht->cell[s][2] = 0u; ht->cell[s][3] = 0u;
+        }
+    }
+}
+#endif
+
 // ---- one round = push, record, pull ------------------------------------------------
 // A round transforms the point, hands it to another thread of the CTA (push ... barrier
 // ... pull) and records one sample.  The sample recorded is the point the thread just
@@ -173,33 +236,44 @@ __device__ __forceinline__ int exchange_slot(int tid, int warp, int lane, int ro
 // mbarrier (arrive, record, wait) was measured too: its polling wait costs more issue
 // slots than the barrier stall it removes (25.0 vs 23.4 ms, G6F).
 // First half of a round: transform this thread's point and publish it.  Returns the
-// warp's random word (its low bits pick the lane that drains packed cells).
+// warp's random word (its low bits pick the lane that drains packed cells); `visible`
+// says whether the new point may be recorded (xform opacity).
 __device__ __forceinline__ unsigned int chaos_push(xchg_buf *xb, int tid, int warp, int lane, int round,
-                                                   float &x, float &y, float &c, mwc_st &rng) {
+                                                   float &x, float &y, float &c, int &last,
+                                                   mwc_st &rng, bool &visible) {
     if (point_is_bad(x, y)) reseed_point(x, y, c, rng);
 
+#if XAOS
+    // the choice depends on the trajectory's previous xform: one random per thread,
+    // and the point stays with its thread (iter.py:236-257)
+    visible = chaos_step(mwc_next_01(rng), x, y, c, last, rng);
+    return (unsigned int)round;
+#else
     // one random word per warp per round (iter.py:197-201,261)
     unsigned int word = 0;
     if (lane == 0) word = mwc_next(rng);
     word = __shfl_sync(0xffffffffu, word, 0);
     float sel = __uint2float_rn(word) * 2.3283064365386962890625e-10f;
-    chaos_step(sel, x, y, c, rng);
+    visible = chaos_step(sel, x, y, c, last, rng);
 
     xchg_buf *b = xb + (round & 1);
     int slot = exchange_slot(tid, warp, lane, round);
     b->xy[slot] = make_float2(x, y);
     b->c[slot] = c;
     return word;
+#endif
 }
 
 // Second half: take the point another thread published this round.
 __device__ __forceinline__ void chaos_pull(xchg_buf *xb, int tid, int round, float &x, float &y, float &c) {
+#if !XAOS
     __syncthreads();
     xchg_buf *b = xb + (round & 1);
     float2 p = b->xy[tid];
     x = p.x;
     y = p.y;
     c = b->c[tid];
+#endif
 }
 
 #if ACC_PACKED
@@ -211,23 +285,39 @@ typedef float4 pal_entry;
 #define RED_BEFORE_PULL 0
 #endif
 
-__device__ __forceinline__ void record_sample(const iter_args &a, int bin, pal_entry col,
-                                              unsigned int word, int lane) {
+struct iter_smem {
+    xchg_buf xb[2];
+    pal_entry pal[256];
+#if HOT_BINS
+    unsigned long long palp[256];       // the unit's palette row as packed 8-bit levels
+    hot_table hot;
+#endif
+};
+
+__device__ __forceinline__ void record_sample(const iter_args &a, iter_smem &sm, int bin,
+                                              unsigned int cidx, unsigned int word, int lane) {
 #if ACC_PACKED
-    accumulate_packed(a.cells + bin, a.hist + bin, col, (word & 31u) == (unsigned int)lane);
+    accumulate_packed(a.cells + bin, a.hist + bin, sm.pal[cidx], (word & 31u) == (unsigned int)lane);
 #else
-    red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), col);
+#if HOT_BINS
+    const unsigned int hs = hot_slot(bin);
+    if (sm.hot.tag[hs] == bin) {
+        const unsigned long long p = sm.palp[cidx];
+        atomicAdd(&sm.hot.cell[hs][0], 1u);
+        atomicAdd(&sm.hot.cell[hs][1], (unsigned int)(p >> 36) & 0xffu);
+        atomicAdd(&sm.hot.cell[hs][2], (unsigned int)(p >> 18) & 0xffu);
+        atomicAdd(&sm.hot.cell[hs][3], (unsigned int)p & 0xffu);
+        return;
+    }
+#endif
+    red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), sm.pal[cidx]);
 #endif
 }
 
 extern "C" __global__ void __launch_bounds__(ITER_THREADS, ITER_MIN_CTAS)
 cb_iter(const __grid_constant__ iter_args a) {
-    __shared__ xchg_buf xb[2];
-#if ACC_PACKED
-    __shared__ unsigned long long s_pal[256];
-#else
-    __shared__ float4 s_pal[256];
-#endif
+    __shared__ iter_smem sm;
+    xchg_buf *xb = sm.xb;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -235,6 +325,7 @@ cb_iter(const __grid_constant__ iter_args a) {
 
     mwc_st rng = a.seeds[gtid];
     float x, y, c;
+    int last = 0;               // iter.py:209
 
     const unsigned long long unit0 = a.first_sample / UNIT_SAMPLES;
     const unsigned long long nunits = (a.nsamples + UNIT_SAMPLES - 1) / UNIT_SAMPLES;
@@ -250,6 +341,13 @@ cb_iter(const __grid_constant__ iter_args a) {
         float4 p = a.points[gtid];
         x = p.x; y = p.y; c = p.z;
     }
+#if HOT_BINS
+    for (int s = tid; s < HOT_SLOTS; s += ITER_THREADS) {
+        sm.hot.tag[s] = a.hot_tags[s];
+        sm.hot.cell[s][0] = 0u; sm.hot.cell[s][1] = 0u; sm.hot.cell[s][2] = 0u; sm.hot.cell[s][3] = 0u;
+    }
+    int units_done = 0;
+#endif
 
     for (unsigned long long lu = blockIdx.x; lu < nunits || fresh; lu += gridDim.x) {
         // temporal sample of this unit: contiguous runs of units per sample
@@ -263,18 +361,26 @@ cb_iter(const __grid_constant__ iter_args a) {
 #endif
         if (row != cur_row) {
 #if ACC_PACKED
-            s_pal[tid] = a.palette_packed[row * 256 + tid];
+            sm.pal[tid] = a.palette_packed[row * 256 + tid];
 #else
-            s_pal[tid] = a.palette[row * 256 + tid];
+            sm.pal[tid] = a.palette[row * 256 + tid];
+#endif
+#if HOT_BINS
+            sm.palp[tid] = a.palette_packed[row * 256 + tid];
 #endif
             cur_row = row;
         }
+#if HOT_BINS
+        if (units_done && units_done % HOT_FLUSH_UNITS == 0) hot_flush(&sm.hot, a, tid);
+        units_done++;
+#endif
         __syncthreads();
 
         if (fresh) {
             // settle new trajectories without recording them (iter.py:211-216)
+            bool vis;
             for (int r = 0; r < a.fuse_rounds; r++, round_ctr++) {
-                chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, rng);
+                chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, last, rng, vis);
                 chaos_pull(xb, tid, round_ctr, x, y, c);
             }
             fresh = false;
@@ -290,13 +396,15 @@ cb_iter(const __grid_constant__ iter_args a) {
         const float color_dither = 0.49f * mwc_next_11(rng);      // iter.py:185
 
         for (int r = 0; r < rounds; r++, round_ctr++) {
-            unsigned int word = chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, rng);
+            bool visible;
+            unsigned int word = chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, last, rng,
+                                           visible);
             // The sample of the point this thread just produced.  Its coordinates are
             // dead once published (the thread continues with the point it receives), so
             // the final xform and the camera run with x, y, c off the register file.
             int bin = -1;
             unsigned int cidx = 0;
-            if (r * ITER_THREADS + tid < live) {
+            if (visible && r * ITER_THREADS + tid < live) {
                 float fx = x, fy = y, fc = c;
 #if HAS_FINAL
                 final_step(fx, fy, fc, rng);
@@ -305,14 +413,18 @@ cb_iter(const __grid_constant__ iter_args a) {
                 cidx = color_index(fc, color_dither);
             }
 #if RED_BEFORE_PULL
-            if (bin >= 0) record_sample(a, bin, s_pal[cidx], word, lane);
+            if (bin >= 0) record_sample(a, sm, bin, cidx, word, lane);
             chaos_pull(xb, tid, round_ctr, x, y, c);
 #else
             chaos_pull(xb, tid, round_ctr, x, y, c);
-            if (bin >= 0) record_sample(a, bin, s_pal[cidx], word, lane);
+            if (bin >= 0) record_sample(a, sm, bin, cidx, word, lane);
 #endif
         }
     }
+#if HOT_BINS
+    __syncthreads();
+    hot_flush(&sm.hot, a, tid);
+#endif
 
     a.points[gtid] = make_float4(x, y, c, 0.0f);
     a.seeds[gtid] = rng;
@@ -328,7 +440,8 @@ __device__ __forceinline__ void probe_load_params(const float *params) {
 // Apply the genome's weighted choice with a given selector to explicit points.
 extern "C" __global__ void cb_probe_xform(const float *params, float *xs, float *ys,
                                           float *cs, mwc_st *seeds, int n, float sel,
-                                          int use_final) {
+                                          int use_final, int last_xf, int *visible,
+                                          int *last_out) {
     probe_load_params(params);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -338,7 +451,12 @@ extern "C" __global__ void cb_probe_xform(const float *params, float *xs, float 
     if (use_final) final_step(x, y, c, rng);
     else
 #endif
-        chaos_step(sel, x, y, c, rng);
+    {
+        int last = last_xf;
+        bool vis = chaos_step(sel, x, y, c, last, rng);
+        if (visible) visible[i] = vis ? 1 : 0;
+        if (last_out) last_out[i] = last;
+    }
     xs[i] = x; ys[i] = y; cs[i] = c;
     seeds[i] = rng;
 }

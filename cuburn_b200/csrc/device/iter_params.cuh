@@ -19,7 +19,14 @@
 __constant__ float c_params[NSLOTS > 0 ? NSLOTS : 1];
 #define P c_params
 #else
-// Motion blur: the CTA stages the block of its unit's temporal sample here.
-__shared__ float s_params[NSLOTS > 0 ? NSLOTS : 1];
+// Motion blur: the CTA stages the block of its unit's temporal sample here; generated
+// code reads it as aligned float4s (P4) where slots are contiguous.
+__shared__ __align__(16) float s_params[(NSLOTS + 3) / 4 * 4 + 4];
 #define P s_params
+#define P4 (reinterpret_cast<const float4 *>(s_params))
 #endif
+
+// xform opacity (genome/specs.py:17): the share of the xform's points that are drawn.
+__device__ __forceinline__ bool opacity_visible(float opacity, mwc_st &rng) {
+    return opacity >= 1.0f || mwc_next_01(rng) < opacity;
+}

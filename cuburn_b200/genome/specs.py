@@ -24,6 +24,11 @@ xform = {
     'color_speed': spline(0.5, 0, 1),
     'weight': spline(),
     'opacity': scalespline(max=1),
+    # xaos: multiplier on the weight of xform n when the trajectory's previous xform was
+    # this one.  The reference reads ``cp.xforms[p].chaos[n]`` (code/iter.py:32-54) and its
+    # converter writes the map (genome/convert.py:182-183), but its schema never got the
+    # entry; it is declared here so the feature can be switched on.
+    'chaos': map_(scalespline()),
     'variations': var_params,
 }
 

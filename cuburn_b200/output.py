@@ -174,7 +174,9 @@ class EncoderPipe(object):
     """
     One external encoder process: raw frames go to its stdin, its stdout is
     collected in an unnamed temporary file (or it writes a named file itself), its
-    stderr becomes the log.  ``finish()`` closes stdin, waits, and returns
+    stderr -- the log -- goes to another temporary file (a pipe that nobody drains
+    fills up after a few hundred frames of ``--log-level debug`` and blocks the
+    encoder, and with it the render loop).  ``finish()`` closes stdin, waits, and returns
     ``(file positioned at 0, log)``; a non-zero exit status is an ``IOError``, as
     in the reference (output.py:172-173, 255-256).
     """
@@ -188,34 +190,40 @@ class EncoderPipe(object):
             self.outf = None
         else:
             self.outf = tempfile.TemporaryFile()
+        self.errf = tempfile.TemporaryFile()
         try:
             self.proc = subprocess.Popen([str(a) for a in argv], stdin=subprocess.PIPE,
-                                         stderr=subprocess.PIPE,
+                                         stderr=self.errf,
                                          stdout=self.outf if self.outf is not None
                                          else subprocess.DEVNULL)
         except OSError as e:
             raise IOError('cannot start %s encoder "%s": %s' % (name, argv[0], e))
-        self._log = []
+
+    def _read_log(self):
+        self.errf.seek(0)
+        return self.errf.read().decode(errors='replace')
 
     def write(self, buf):
         try:
             self.proc.stdin.write(memoryview(np.ascontiguousarray(buf)).cast('B'))
         except (IOError, OSError) as e:
+            self.proc.wait()
             raise IOError('%s stopped reading frames: %s\n%s'
-                          % (self.name, e, self.proc.stderr.read().decode(errors='replace')))
+                          % (self.name, e, self._read_log()))
 
     def finish(self):
-        _, log = self.proc.communicate()
+        self.proc.communicate()
+        log = self._read_log()
+        self.errf.close()
         if self.proc.returncode:
-            raise IOError('%s exited with an error\n%s'
-                          % (self.name, log.decode(errors='replace')))
+            raise IOError('%s exited with an error\n%s' % (self.name, log))
         if self.named is not None:
             outf = open(self.named.name, 'rb')      # a new handle; the name goes away
             self.named.close()
         else:
             outf = self.outf
             outf.seek(0)
-        return outf, log.decode(errors='replace')
+        return outf, log
 
 
 class X264Output(Output):

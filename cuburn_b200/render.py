@@ -207,8 +207,9 @@ class Renderer(object):
         return mod
 
     @classmethod
-    def compile(cls, gnm, arch=None, keep=False, params_const=False, acc_packed=False):
-        pk, src = itergen.mkiterlib(gnm, params_const, acc_packed)
+    def compile(cls, gnm, arch=None, keep=False, params_const=False, acc_packed=False,
+                hot_bins=False):
+        pk, src = itergen.mkiterlib(gnm, params_const, acc_packed, hot_bins)
         mod = cls._module(src)
         if keep:
             import os, tempfile
@@ -222,7 +223,10 @@ class Renderer(object):
     def __init__(self, gnm, gprof, keep=False, arch=None):
         self._gnm_structure, self._keep = gnm, keep
         self.packer, self.lib, self.mod = self.compile(gnm, arch=arch, keep=keep)
-        self._variants = {(False, False): self.mod}
+        self._variants = {(False, False, False): self.mod}
+        # hot-bin state of this genome: None = not yet probed, else whether the last
+        # probe found bins hot enough to privatise (RenderManager._iter)
+        self.hot = None
         self.filts = filters.create(gprof)
         self.out = output.get_output_for_profile(gprof)
         self._grid = {}
@@ -231,13 +235,14 @@ class Renderer(object):
     def cubin(self):
         return self.mod.cubin
 
-    def variant(self, params_const, acc_packed=False):
+    def variant(self, params_const, acc_packed=False, hot_bins=False):
         """The iterate module for (parameters in __constant__ memory?, packed u64
-        accumulation?), compiled on first use."""
-        key = (bool(params_const), bool(acc_packed))
+        accumulation?, private shared-memory cells for hot bins?), compiled on first
+        use."""
+        key = (bool(params_const), bool(acc_packed), bool(hot_bins))
         if key not in self._variants:
             self._variants[key] = self.compile(self._gnm_structure, params_const=key[0],
-                                               acc_packed=key[1])[2]
+                                               acc_packed=key[1], hot_bins=key[2])[2]
         return self._variants[key]
 
     @property
@@ -265,7 +270,8 @@ class RenderManager(object):
         if world > 1:
             # disjoint RNG streams per GPU (multigpu.make_rank_seeds)
             from .multigpu import make_rank_seeds
-            N.memcpy_htod(self.fb.d_seeds, make_rank_seeds(rank, world, seed or 1,
+            N.memcpy_htod(self.fb.d_seeds, make_rank_seeds(rank, world,
+                                                           1 if seed is None else seed,
                                                            self.fb.nstreams))
         self.src_a, self.src_b = DevSrc(), DevSrc()
         self.info_a, self.info_b = DevInfo(), DevInfo()
@@ -273,6 +279,10 @@ class RenderManager(object):
         self.filt_evt = self.copy_evt = None
         import collections
         self._pinned = collections.deque(maxlen=4)
+        # hot-bin table: u64 scratch[512] | int32 tags[512] | int32 count
+        self.d_hot = N.DeviceBuffer(512 * 8 + 512 * 4 + 16)
+        N.fill32(self.d_hot, (512 * 8 + 512 * 4 + 16) // 4, 0)
+        self._hot_probe = None          # (event, pinned count, renderer) of the last scan
         # share of the frame's samples this manager renders (multi-GPU stills)
         self.sample_share = (rank, world)
         self.hist_hook = None
@@ -371,6 +381,47 @@ class RenderManager(object):
             return 16 * nbins > 1.5 * self._l2_bytes
         return self.accumulate == 'packed'
 
+    # Bins that collect more than ``hot_share`` of the samples are bound by the rate of
+    # one histogram address (~6.5e8 reductions/s); the frame's first ``1/hot_pilot`` of
+    # samples is rendered as a pilot, cb_hot_scan lists such bins, and the rest of the
+    # frame runs the HOT_BINS variant, which accumulates them in shared memory.  'auto':
+    # probe every genome once (one host sync on a renderer's first frame), afterwards
+    # follow the previous frame's scan without synchronising.  False: never; True:
+    # always run the pilot and the HOT_BINS variant.
+    hot_bins = 'auto'
+    hot_share = 1.0 / 2048
+    hot_pilot = 64
+    hot_min_units = 256
+
+    def _launch_iter(self, mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
+                     hot, s):
+        args = N.IterArgs(
+            hist=int(d_acc), swizzle_bins=swz, seeds=self.fb.d_seeds.ptr,
+            points=self.fb.d_points.ptr, params=info.d_params.ptr,
+            palette=info.d_palette.ptr, dim=dim, param_stride=rdr.packer.param_stride,
+            nts=info.ntemporal_samples, pal_rows=info.palette_height,
+            fuse_rounds=fuse, first_sample=first, nsamples=n, total_samples=total,
+            cells=self.fb.d_left.ptr if packed else 0,
+            palette_packed=info.d_palette_packed.ptr,
+            hot_tags=self.d_hot.ptr + 512 * 8 if hot else 0)
+        N.check(N.lib().cb_iterate(mod.handle, N.byref(args),
+                                   rdr.grid_ctas(self.fb.nstreams, mod), s.handle))
+
+    def _hot_decision(self, rdr, nunits, packed):
+        """(run the pilot + scan?, use the HOT_BINS variant?) for this frame."""
+        if packed or self.hot_bins is False or nunits < self.hot_min_units:
+            return False, False
+        if self.hot_bins is True:
+            return True, True
+        # 'auto': take in the result of the last scan if it has completed
+        if self._hot_probe is not None and self._hot_probe[2] is rdr:
+            evt, count, _ = self._hot_probe
+            if evt.query():
+                rdr.hot = bool(count[0] > 0)
+        if rdr.hot is None:
+            return True, None               # first frame of this genome: probe and wait
+        return True, rdr.hot
+
     def _iter(self, rdr, gnm, gprof, dim, tc):
         s, info = self.stream_a, self.info_a
         nbins = dim.ah * dim.astride
@@ -384,26 +435,48 @@ class RenderManager(object):
         # without motion blur all temporal samples are identical: use the variant
         # that reads one parameter block from __constant__ memory
         still = gprof.frame_width(tc) == 0
+        nunits = (n + UNIT_SAMPLES - 1) // UNIT_SAMPLES
+        pilot, hot = self._hot_decision(rdr, nunits, packed)
         mod = rdr.variant(still, packed)
         if still:
             mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
-        args = N.IterArgs(
-            hist=int(d_acc), swizzle_bins=swz, seeds=self.fb.d_seeds.ptr,
-            points=self.fb.d_points.ptr, params=info.d_params.ptr,
-            palette=info.d_palette.ptr, dim=dim, param_stride=rdr.packer.param_stride,
-            nts=info.ntemporal_samples, pal_rows=info.palette_height,
-            fuse_rounds=info.fuse, first_sample=first, nsamples=n, total_samples=total,
-            cells=self.fb.d_left.ptr if packed else 0,
-            palette_packed=info.d_palette_packed.ptr)
-        N.check(N.lib().cb_iterate(mod.handle, N.byref(args),
-                                   rdr.grid_ctas(self.fb.nstreams, mod), s.handle))
+        fuse = info.fuse
+        n_frame = n
+        if pilot:
+            # whole waves of the persistent grid, about 1/hot_pilot of the frame
+            grid = rdr.grid_ctas(self.fb.nstreams, mod)
+            npilot = grid * max(1, round(nunits / float(self.hot_pilot * grid))) * UNIT_SAMPLES
+            npilot = min(npilot, (nunits // 2) * UNIT_SAMPLES)
+            self._launch_iter(mod, rdr, info, d_acc, swz, dim, first, npilot, total, fuse,
+                              packed, False, s)
+            d_tags, d_count = self.d_hot.ptr + 512 * 8, self.d_hot.ptr + 512 * 8 + 512 * 4
+            N.check(N.lib().cb_hot_scan(d_tags, d_count, self.d_hot.ptr, int(d_acc), swz,
+                                        np.float32(max(32.0, self.hot_share * npilot)),
+                                        N.byref(dim), s.handle))
+            count = self.fb.pool.allocate((1,), 'i4')
+            N.memcpy_dtoh(count, N.DeviceSlice(self.d_hot, 512 * 8 + 512 * 4, 4), s)
+            evt = N.Event().record(s)
+            self._hot_probe = (evt, count, rdr)
+            self._pinned.append((count,))
+            if hot is None:
+                evt.synchronize()
+                hot = rdr.hot = bool(count[0] > 0)
+            first, n, fuse = first + npilot, n - npilot, 0
+        if hot:
+            mod = rdr.variant(still, packed, True)
+            if still:
+                mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
+        if n > 0:
+            self._launch_iter(mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
+                              bool(hot), s)
         if packed:
             N.check(N.lib().cb_flush_packed(self.fb.d_front.ptr, self.fb.d_left.ptr,
                                             N.byref(dim), s.handle))
         if swz:
             N.check(N.lib().cb_hist_unswizzle(int(self.fb.d_front), int(d_acc), swz,
                                               N.byref(dim), s.handle))
-        self.last_iter_samples = n
+        self.last_iter_samples = n_frame
+        self.last_iter_hot = bool(hot)
 
     # -- filter ----------------------------------------------------------------------
     # multi-GPU stills: a multigpu.BandFilter makes every GPU filter a band of rows
@@ -432,9 +505,14 @@ class RenderManager(object):
         """
         timing_event = N.Event().record(self.stream_b)
         if frame_seed is not None:
-            from . import mwc as _mwc
             seeds = self.fb.pool.allocate((self.fb.nstreams, 3), 'u4')
-            seeds[:] = _mwc.make_seeds(self.fb.nstreams, host_seed=int(frame_seed))
+            rank, world = self.sample_share
+            if world > 1:
+                # a sample-split still: every GPU needs its own streams for the frame
+                from .multigpu import make_rank_seeds
+                seeds[:] = make_rank_seeds(rank, world, int(frame_seed), self.fb.nstreams)
+            else:
+                seeds[:] = mwc.make_seeds(self.fb.nstreams, host_seed=int(frame_seed))
             # the seed table is shared with the previous frame (which ran on stream_b
             # and still dithers its output from it): order this upload after it
             self.stream_a.wait_for_event(N.Event().record(self.stream_b))
@@ -448,9 +526,12 @@ class RenderManager(object):
         if copy:
             self.src_a, self.src_b = self.src_b, self.src_a
             self._copy(rdr, gnm)
-        self._interp(rdr, gnm, dim, ts, td)
+        # the previous frame (other stream) owns the framebuffers and the RNG streams
+        # until its conversion has run: cb_interp_palette advances the same seed table
+        # that frame's cb_iter / cb_convert read and write back
         if self.filt_evt:
             self.stream_a.wait_for_event(self.filt_evt)
+        self._interp(rdr, gnm, dim, ts, td)
         self._iter(rdr, gnm, gprof, dim, tc)
         if self.hist_hook is not None:
             # multi-GPU stills: combine per-GPU histograms before filtering

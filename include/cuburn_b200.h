@@ -157,8 +157,9 @@ typedef struct {
     uint64_t total_samples;  /* samples of the whole frame, all calls/GPUs */
     cb_dptr cells;           /* packed-accumulator module only: u64 [aheight][astride]
                                 cells (count:10 | Y:18 | U:18 | V:18, iter.py:334-407) */
-    cb_dptr palette_packed;  /* packed-accumulator module only: u64 [pal_rows][256]
+    cb_dptr palette_packed;  /* packed-accumulator and hot-bin modules: u64 [pal_rows][256]
                                 from cb_palette_pack */
+    cb_dptr hot_tags;        /* hot-bin module only: int32 [512] from cb_hot_scan */
 } cb_iter_args;
 /* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
  * accumulated into hist.  grid_ctas persistent CTAs of 256 threads; work is
@@ -173,6 +174,18 @@ int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas,
  * cb_flush_packed is flush_atom (iter.py:420-479): hist[i] += unpack(cells[i]). */
 int cb_palette_pack(cb_dptr palette_packed, cb_dptr palette4, int nrows, cb_stream s);
 int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream s);
+
+/* Hot bins.  A single histogram address absorbs ~6.5e8 reductions/s, so flames with very
+ * bright bins are bound by those bins; the reference thins them (hotspot flags written
+ * by flush_atom, iter.py:481-526, consumed at iter.py:319-329).  Here: after a short
+ * pilot pass of cb_iterate, cb_hot_scan enters every bin of `hist4` (layout as
+ * accumulated: swizzle_bins as in cb_iter_args) holding >= threshold samples into a
+ * 512-slot table `tags` (bin index or -1; the hotter bin wins a shared slot) and writes
+ * the number of entries to `count`; `scratch` is 512 zeroed u64 (left zeroed).  The
+ * HOT_BINS variant of the iterate module accumulates those bins in shared memory as
+ * integer level sums and folds them into the histogram itself. */
+int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
+                int swizzle_bins, float threshold, const cb_dims *dim, cb_stream s);
 
 /* Undo the accumulation layout: dst[i] = src[swizzle(i)] for i < swizzle_bins,
  * dst[i] = src[i] above; dst is the linear float4 [aheight][astride] histogram the

@@ -18,6 +18,12 @@ def pytest_configure(config):
 def native():
     """The C-ABI library initialised on cuda:0 (GPU tests only)."""
     from cuburn_b200 import _native as N
+    try:
+        ndev = N.device_count()
+    except Exception as e:          # no driver on this host
+        pytest.skip('no CUDA driver: %s' % e)
+    if ndev < 1:
+        pytest.skip('no CUDA device')
     N.init(0)
     return N
 

@@ -156,7 +156,7 @@ def test_variation_matches_oracle(native, built, name):
     mod.launch('cb_probe_xform', ((n + 255) // 256,), (256,),
                [c.c_uint64(d_par.ptr), c.c_uint64(d_x.ptr), c.c_uint64(d_y.ptr),
                 c.c_uint64(d_c.ptr), c.c_uint64(d_s.ptr), c.c_int(n), c.c_float(0.0),
-                c.c_int(0)])
+                c.c_int(0), c.c_int(0), c.c_uint64(0), c.c_uint64(0)])
     N.check(N.lib().cb_device_sync())
     gxs, gys, gcs = (N.from_device(b, (n,), np.float32) for b in (d_x, d_y, d_c))
     gseeds = N.from_device(d_s, (n, 3), np.uint32)

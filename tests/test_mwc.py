@@ -114,3 +114,12 @@ def test_device_mwc_matches_model(native, built):
     after = N.from_device(d_seeds, (n, 3), np.uint32)
     assert np.array_equal(want, got)
     assert np.array_equal(after[:, 1], st) and np.array_equal(after[:, 2], ca)
+
+
+def test_seed_zero_is_a_seed(built):
+    """Seed 0 (a natural frame index) must be reproducible; the reference treats it as
+    "no seed" (code/mwc.py:39), which is kept only for ``None``."""
+    from cuburn_b200 import mwc
+    a, b = mwc.make_seeds(64, host_seed=0), mwc.make_seeds(64, host_seed=0)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a[:, 1:], mwc.make_seeds(64, host_seed=1)[:, 1:])
