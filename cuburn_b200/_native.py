@@ -60,7 +60,8 @@ class IterArgs(ctypes.Structure):
                 ('pal_rows', c_int32), ('fuse_rounds', c_int32), ('swizzle_bins', c_int32),
                 ('first_sample', c_uint64), ('nsamples', c_uint64),
                 ('total_samples', c_uint64), ('cells', c_uint64),
-                ('palette_packed', c_uint64), ('hot_tags', c_uint64)]
+                ('palette_packed', c_uint64), ('hot_tags', c_uint64),
+                ('first_round', c_int32)]
 
 
 _SIGNATURES = {

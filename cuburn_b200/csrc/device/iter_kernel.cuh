@@ -61,6 +61,7 @@ struct iter_args {
     unsigned long long *cells;                 // ACC_PACKED: u64 [aheight][astride]
     const unsigned long long *palette_packed;  // ACC_PACKED / HOT_BINS: u64 [pal_rows][256]
     const int *hot_tags;                       // HOT_BINS: int [HOT_SLOTS], bin or -1
+    int first_round;        // phase of the exchange permutation to start from
 };
 
 #ifndef ACC_PACKED
@@ -332,7 +333,7 @@ cb_iter(const __grid_constant__ iter_args a) {
     const unsigned long long frame_units =
         (a.total_samples + UNIT_SAMPLES - 1) / UNIT_SAMPLES;
 
-    int round_ctr = 0;
+    int round_ctr = a.first_round;
     int cur_row = -1;
     bool fresh = a.fuse_rounds > 0;
     if (fresh) {
@@ -472,4 +473,17 @@ extern "C" __global__ void cb_probe_bins(const float *params, const float *xs,
     bins[i] = sample_bin(xs[i], ys[i], astride, aheight);
     cidx[i] = (int)color_index(cs[i], dithers[i]);
 }
+
+#if ACC_PACKED
+// Packed accumulation of an explicit sample list: thread i adds palette entry cidx[i]
+// to bin bins[i], draining the cell when drain[i] is set.
+extern "C" __global__ void cb_probe_accumulate(unsigned long long *cells, float4 *hist,
+                                               const int *bins, const int *cidx,
+                                               const int *drain, const unsigned long long *pal,
+                                               int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    accumulate_packed(cells + bins[i], hist + bins[i], pal[cidx[i]], drain[i] != 0);
+}
+#endif
 #endif

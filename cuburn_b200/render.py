@@ -391,10 +391,10 @@ class RenderManager(object):
     hot_bins = 'auto'
     hot_share = 1.0 / 2048
     hot_pilot = 64
-    hot_min_units = 256
+    hot_min_waves = 4               # frames shorter than this many waves of units: never
 
     def _launch_iter(self, mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
-                     hot, s):
+                     hot, s, first_round=0):
         args = N.IterArgs(
             hist=int(d_acc), swizzle_bins=swz, seeds=self.fb.d_seeds.ptr,
             points=self.fb.d_points.ptr, params=info.d_params.ptr,
@@ -403,13 +403,13 @@ class RenderManager(object):
             fuse_rounds=fuse, first_sample=first, nsamples=n, total_samples=total,
             cells=self.fb.d_left.ptr if packed else 0,
             palette_packed=info.d_palette_packed.ptr,
-            hot_tags=self.d_hot.ptr + 512 * 8 if hot else 0)
+            hot_tags=self.d_hot.ptr + 512 * 8 if hot else 0, first_round=first_round)
         N.check(N.lib().cb_iterate(mod.handle, N.byref(args),
                                    rdr.grid_ctas(self.fb.nstreams, mod), s.handle))
 
-    def _hot_decision(self, rdr, nunits, packed):
+    def _hot_decision(self, rdr, nunits, packed, grid):
         """(run the pilot + scan?, use the HOT_BINS variant?) for this frame."""
-        if packed or self.hot_bins is False or nunits < self.hot_min_units:
+        if packed or self.hot_bins is False or nunits < self.hot_min_waves * grid:
             return False, False
         if self.hot_bins is True:
             return True, True
@@ -436,17 +436,16 @@ class RenderManager(object):
         # that reads one parameter block from __constant__ memory
         still = gprof.frame_width(tc) == 0
         nunits = (n + UNIT_SAMPLES - 1) // UNIT_SAMPLES
-        pilot, hot = self._hot_decision(rdr, nunits, packed)
         mod = rdr.variant(still, packed)
+        grid = rdr.grid_ctas(self.fb.nstreams, mod)
+        pilot, hot = self._hot_decision(rdr, nunits, packed, grid)
         if still:
             mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
-        fuse = info.fuse
+        fuse, first_round = info.fuse, 0
         n_frame = n
         if pilot:
             # whole waves of the persistent grid, about 1/hot_pilot of the frame
-            grid = rdr.grid_ctas(self.fb.nstreams, mod)
             npilot = grid * max(1, round(nunits / float(self.hot_pilot * grid))) * UNIT_SAMPLES
-            npilot = min(npilot, (nunits // 2) * UNIT_SAMPLES)
             self._launch_iter(mod, rdr, info, d_acc, swz, dim, first, npilot, total, fuse,
                               packed, False, s)
             d_tags, d_count = self.d_hot.ptr + 512 * 8, self.d_hot.ptr + 512 * 8 + 512 * 4
@@ -461,6 +460,8 @@ class RenderManager(object):
             if hot is None:
                 evt.synchronize()
                 hot = rdr.hot = bool(count[0] > 0)
+            # the pilot is whole waves: every CTA has run the same number of rounds
+            first_round = fuse + (npilot // UNIT_SAMPLES // grid) * (UNIT_SAMPLES // ITER_THREADS)
             first, n, fuse = first + npilot, n - npilot, 0
         if hot:
             mod = rdr.variant(still, packed, True)
@@ -468,7 +469,7 @@ class RenderManager(object):
                 mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
         if n > 0:
             self._launch_iter(mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
-                              bool(hot), s)
+                              bool(hot), s, first_round)
         if packed:
             N.check(N.lib().cb_flush_packed(self.fb.d_front.ptr, self.fb.d_left.ptr,
                                             N.byref(dim), s.handle))

@@ -151,4 +151,15 @@ def g24h():
     }
 
 
-GENOMES = {'G3': g3, 'G6F': g6f, 'G24H': g24h}
+def g2m():
+    """The hot-spot probe: G6F cut down to its first two (contractive) xforms, no final
+    xform.  A handful of bins collect several per cent of all samples, which makes the
+    frame bound by single-address atomic throughput unless those bins are privatised."""
+    g = g6f()
+    g['name'] = 'G2M'
+    g['xforms'] = dict((k, v) for k, v in g['xforms'].items() if int(k) < 2)
+    g.pop('final_xform')
+    return g
+
+
+GENOMES = {'G3': g3, 'G6F': g6f, 'G24H': g24h, 'G2M': g2m}

@@ -160,6 +160,9 @@ typedef struct {
     cb_dptr palette_packed;  /* packed-accumulator and hot-bin modules: u64 [pal_rows][256]
                                 from cb_palette_pack */
     cb_dptr hot_tags;        /* hot-bin module only: int32 [512] from cb_hot_scan */
+    int32_t first_round;     /* rounds every CTA has run in earlier calls of this frame
+                                (fuse rounds included): a frame split over several calls
+                                then draws the same samples as one call would */
 } cb_iter_args;
 /* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
  * accumulated into hist.  grid_ctas persistent CTAs of 256 threads; work is

@@ -34,15 +34,93 @@ def available():
     return os.path.exists(LIB) and os.path.exists(META)
 
 
+def _sample_genomes():
+    """Genome structures the iterate functions are rendered for (the synthetic test
+    genomes: BASELINE configs 1-5 plus one with a post-affine and no final xform)."""
+    import sys
+    root = os.path.dirname(HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from cuburn_b200 import samples
+    return {'g3': samples.g3(), 'g6f': samples.g6f(), 'g24h': samples.g24h()}
+
+
 class _Template(object):
-    """Stand-in for tempita.Template: keeps the raw text; renders ``{{expr}}``
-    placeholders by evaluating them against the arguments, and un-nested
-    ``{{for x in expr}} ... {{endfor}}`` loops (what precalc_densities needs); any
-    other control flow is refused."""
-    _LOOP = re.compile(r'\{\{for (\w+) in (.*?)\}\}(.*?)\{\{endfor\}\}', re.S)
+    """Stand-in for tempita.Template, enough of it for the reference's device code:
+    ``{{expr}}`` (``None`` renders as nothing), ``{{for a, b in expr}} ... {{endfor}}``,
+    ``{{if expr}} ... {{elif expr}} ... {{else}} ... {{endif}}`` and ``{{py: stmt}}``,
+    nested to any depth.  Expressions see the substitution arguments, the template's
+    namespace and the variables bound by enclosing loops; ``locals()`` inside an
+    expression is that combined scope (iter.py renders the variation bodies with it)."""
+    _TOKEN = re.compile(r'\{\{(.*?)\}\}', re.S)
 
     def __init__(self, content, name=None, namespace=None, **kw):
         self.content, self.name, self.namespace = content, name, namespace or {}
+
+    def _parse(self):
+        pos, stack = 0, [[]]         # stack of open blocks; a block is a list of nodes
+        heads = []
+        for m in self._TOKEN.finditer(self.content):
+            if m.start() > pos:
+                stack[-1].append(('text', self.content[pos:m.start()]))
+            pos = m.end()
+            tok = m.group(1).strip()
+            if tok.startswith('for '):
+                var, expr = tok[4:].split(' in ', 1)
+                node = ('for', [v.strip() for v in var.split(',')], expr, [])
+                stack[-1].append(node)
+                stack.append(node[3])
+                heads.append(node)
+            elif tok.startswith('if '):
+                node = ('if', [(tok[3:], [])])
+                stack[-1].append(node)
+                stack.append(node[1][0][1])
+                heads.append(node)
+            elif tok.startswith('elif ') or tok == 'else':
+                node = heads[-1]
+                assert node[0] == 'if', 'stray %s in template %s' % (tok, self.name)
+                stack.pop()
+                node[1].append((tok[5:] if tok != 'else' else 'True', []))
+                stack.append(node[1][-1][1])
+            elif tok in ('endfor', 'endif'):
+                assert heads and heads[-1][0] == tok[3:], 'unbalanced %s in %s' % (tok, self.name)
+                heads.pop()
+                stack.pop()
+            elif tok.startswith('py:'):
+                stack[-1].append(('py', tok[3:].strip()))
+            else:
+                stack[-1].append(('expr', tok))
+        if pos < len(self.content):
+            stack[-1].append(('text', self.content[pos:]))
+        assert len(stack) == 1, 'unclosed block in template %s' % self.name
+        return stack[0]
+
+    def _render(self, nodes, ns):
+        out = []
+        for node in nodes:
+            kind = node[0]
+            if kind == 'text':
+                out.append(node[1])
+            elif kind == 'expr':
+                val = eval(node[1], ns)
+                out.append('' if val is None else str(val))
+            elif kind == 'py':
+                exec(node[1], ns)
+            elif kind == 'for':
+                _, names, expr, body = node
+                for item in list(eval(expr, ns)):
+                    if len(names) == 1:
+                        ns[names[0]] = item
+                    else:
+                        for n, v in zip(names, item):
+                            ns[n] = v
+                    out.append(self._render(body, ns))
+            elif kind == 'if':
+                for cond, body in node[1]:
+                    if eval(cond, ns):
+                        out.append(self._render(body, ns))
+                        break
+        return ''.join(out)
 
     def substitute(self, *a, **kw):
         ns = dict(self.namespace)
@@ -50,20 +128,7 @@ class _Template(object):
             if isinstance(d, dict):
                 ns.update(d)
         ns.update(kw)
-
-        def fill(text, scope):
-            return re.sub(r'\{\{(.*?)\}\}', lambda m: str(eval(m.group(1), scope)), text)
-
-        def loop(m):
-            var, expr, body = m.groups()
-            if '{{for' in body:
-                raise RuntimeError('template %s nests loops' % self.name)
-            return ''.join(fill(body, dict(ns, **{var: item})) for item in eval(expr, ns))
-
-        text = self._LOOP.sub(loop, self.content)
-        if '{{for' in text or '{{if' in text or '{{py:' in text:
-            raise RuntimeError('template %s uses control flow' % self.name)
-        return fill(text, ns)
+        return self._render(self._parse(), ns)
 
 
 class _FakeNode(object):
@@ -113,6 +178,156 @@ class _FakeXforms(object):
 
     def __getitem__(self, name):
         return getattr(self._node, name)
+
+
+class _View(object):
+    """
+    Stand-in for the packer view (PackerWrapper / PrecalcWrapper, code/interp.py:28-123) that
+    the iterate templates are rendered against.  A node is a genome path; coercing it to a
+    string yields the C identifier of that parameter: ``out_<path>`` when a precalc hunk
+    has produced it with ``_set`` (rendered earlier in the same template, as in the
+    reference), else ``in_<path>``, an input of the generated function.  Container
+    emulation follows genome/use.py:90-99 (sorted keys).
+    """
+    def __init__(self, path, reg, present):
+        self.__dict__.update(_path=tuple(path), _reg=reg, _present=present)
+
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return _View(self._path + (name,), self._reg, self._present)
+
+    def __getitem__(self, name):
+        return getattr(self, str(name))
+
+    def __contains__(self, name):
+        return self._path + (str(name),) in self._present
+
+    def keys(self):
+        n = len(self._path)
+        return sorted(set(p[n] for p in self._present if len(p) > n and p[:n] == self._path))
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def _precalc(self):
+        return self
+
+    def _set(self, name):
+        path = self._path + (name,)
+        if path not in self._reg['out']:
+            self._reg['out'].append(path)
+        return 'out_' + '_'.join(path)
+
+    def _code(self, code):
+        self._reg['codes'].append(code)
+
+    def __str__(self):
+        if self._path in self._reg['out']:
+            return 'out_' + '_'.join(self._path)
+        if self._path not in self._reg['in']:
+            self._reg['in'].append(self._path)
+        return 'in_' + '_'.join(self._path)
+
+
+def _present_paths(root, doc):
+    out = set()
+
+    def walk(path, d):
+        out.add(path)
+        if isinstance(d, dict):
+            for k, v in d.items():
+                walk(path + (str(k),), v)
+    walk((root,), doc)
+    return out
+
+
+def _iterate_functions(itermod, tag, gnm):
+    """
+    The reference's own text of the per-xform functions (``apply_xf_<id>``,
+    code/iter.py:121-149, with the variation bodies and affine precalcs it pulls in), the
+    xform choice chain (iter.py:263-272) and the final xform + camera + `trunca` + bounds
+    test (iter.py:302-317), rendered for genome ``gnm`` and wrapped for the CPU:
+
+      ref_<tag>_setup(in[])                 load the genome's direct parameters, run the precalcs
+      ref_<tag>_apply(xf, x[], y[], c[], seeds[], n)      xf = index in sorted order, -1 = final
+      ref_<tag>_choose(sel, x[], y[], c[], seeds[], last[], n)
+      ref_<tag>_bin(x[], y[], c[], seeds[], idx[], cc[], n)   idx = -1 when rejected
+    Returns (C++ source, [input paths in order]).
+    """
+    reg = {'in': [], 'out': [], 'codes': []}
+    present = _present_paths('cp', gnm)
+    cp = _View(('cp',), reg, present)
+    xids = cp.xforms.keys()
+    bodies = [itermod.iter_xf_body(cp, xid, cp.xforms[xid]) for xid in xids]
+    has_final = 'final_xform' in gnm
+    if has_final:
+        bodies.append(itermod.iter_xf_body(cp, 'final', cp.final_xform))
+    itermod.precalc_camera(cp.camera)
+    itermod.precalc_densities(cp)
+    body = itermod.iter_body_code
+    a0 = body.index("float xfsel = cosel[threadIdx.y];")
+    a1 = body.index("// Rotate points between threads.")
+    chain = '{{py:xk = cp.xforms.keys()}}' + body[a0 + len("float xfsel = cosel[threadIdx.y];"):a1]
+    b0 = body.index("float cx, cy, cc;")
+    b1 = body.index("uint32_t hotspot_i = (")
+    binseg = body[b0:b1].replace('continue;', 'return -1;')
+    ns = dict(itermod.__dict__, cp=cp)
+    chain_c = _Template(chain, tag + '_chain').substitute(ns)
+    bin_c = _Template(binseg, tag + '_bin').substitute(ns)
+    ins, outs = list(reg['in']), list(reg['out'])
+    L = ['namespace ref_%s {' % tag]
+    L += ['static float in_%s;' % '_'.join(p) for p in ins]
+    L += ['static float out_%s;' % '_'.join(p) for p in outs]
+    L += [b.replace('__device__', 'static') for b in bodies]
+    L.append('static int choose(float xfsel, float &x, float &y, float &color, mwc_st &rctx) {\n'
+             '    int last_xf_used = 0;\n%s\n    return last_xf_used;\n}' % chain_c)
+    L.append('static int bin(float x, float y, float color, mwc_st &rctx, float &cc_out) {\n%s\n'
+             '    cc_out = cc;\n    return (int)(iy * acc_size.astride + ix);\n}' % bin_c)
+    L.append('static void setup(const float *in) {')
+    L += ['    in_%s = in[%d];' % ('_'.join(p), i) for i, p in enumerate(ins)]
+    L += ['    {\n%s\n    }' % c for c in reg['codes']]
+    L.append('}')
+    L.append('}  // namespace')
+    calls = ''.join('        case %d: ref_%s::apply_xf_%s(x[i], y[i], c[i], r); break;\n' % (k, tag, xid)
+                    for k, xid in enumerate(xids))
+    if has_final:
+        calls += '        case -1: ref_%s::apply_xf_final(x[i], y[i], c[i], r); break;\n' % tag
+    L.append("""
+extern "C" void ref_%(t)s_setup(const float *in, int width, int awidth, int aheight, int astride) {
+    acc_size.width = width; acc_size.awidth = awidth; acc_size.aheight = aheight;
+    acc_size.astride = astride;
+    ref_%(t)s::setup(in);
+}
+extern "C" void ref_%(t)s_apply(int xf, float *x, float *y, float *c, uint32_t *seeds, int n) {
+    for (int i = 0; i < n; i++) {
+        mwc_st r = {seeds[3*i], seeds[3*i+1], seeds[3*i+2]};
+        switch (xf) {
+%(calls)s        }
+        seeds[3*i+1] = r.state; seeds[3*i+2] = r.carry;
+    }
+}
+extern "C" void ref_%(t)s_choose(float sel, float *x, float *y, float *c, uint32_t *seeds,
+                                 int *last, int n) {
+    for (int i = 0; i < n; i++) {
+        mwc_st r = {seeds[3*i], seeds[3*i+1], seeds[3*i+2]};
+        last[i] = ref_%(t)s::choose(sel, x[i], y[i], c[i], r);
+        seeds[3*i+1] = r.state; seeds[3*i+2] = r.carry;
+    }
+}
+extern "C" void ref_%(t)s_bin(const float *x, const float *y, const float *c, uint32_t *seeds,
+                              int *idx, float *cc, int n) {
+    for (int i = 0; i < n; i++) {
+        mwc_st r = {seeds[3*i], seeds[3*i+1], seeds[3*i+2]};
+        idx[i] = ref_%(t)s::bin(x[i], y[i], c[i], r, cc[i]);
+        seeds[3*i+1] = r.state; seeds[3*i+2] = r.carry;
+    }
+}
+""" % dict(t=tag, calls=calls))
+    return '\n'.join(L), ['.'.join(p[1:]) for p in ins]
 
 
 def _precalc_function(cname, codes, reg, extra_args=''):
@@ -396,6 +611,30 @@ extern "C" void ref_catmull_rom(const float *times, const float *knots, const fl
         parts.append(_precalc_function('ref_precalc_' + vname, codes, reg))
         meta['precalc'][vname] = reg
 
+    # the iterate kernel's own text: apply_xf_<id>, the choice chain, camera + trunca
+    # + bounds (code/iter.py:121-149, 263-272, 302-317), rendered for the sample genomes
+    parts.append('static inline uint32_t trunca(float f) {   // cvt.rni.s32.f32 (util.py:194-200;\n'
+                 '    // the instruction itself is executed by oracle/ptx_emu.py)\n'
+                 '    if (f != f) return 0u;\n'
+                 '    if (f >= 2147483648.0f) return 0x7fffffffu;\n'
+                 '    if (f <= -2147483648.0f) return 0x80000000u;\n'
+                 '    return (uint32_t)(int32_t)nearbyintf(f);\n}')
+    meta['iterate'] = {}
+    for tag, gnm in _sample_genomes().items():
+        code, inputs = _iterate_functions(itermod, tag, gnm)
+        parts.append(code)
+        meta['iterate'][tag] = inputs
+    # inline PTX kept as text: executed by oracle/ptx_emu.py
+    blocks = re.findall(r'\{\{crep\("""(.*?)"""\)\}\}', itermod.iter_body_code, re.S)
+    usrc_ = open(REF + 'util.py').read()
+    meta['ptx'] = {
+        'iter_accumulate': blocks[0],       # code/iter.py:332-407; %0..%7 = cc, color_dither,
+                                            # time, i, atom_ptr, cosel, out_ptr, hotspot_mult
+        'flush_atom': blocks[1],            # code/iter.py:429-540; %0..%6 = gi, hoti, atom_ptr,
+                                            # out_ptr, hotspot_ptr, xi, yi
+        'trunca': re.search(r'asm\("(cvt\.rni\.s32\.f32[^"]*)"', usrc_).group(1),
+    }
+
     # colour helpers (code/color.py:12-42)
     color = _exec_reference('color.py', {'util': util_stub, 'numpy': __import__('numpy')})
     parts.append(color.yuvlib.decls)
@@ -605,3 +844,57 @@ def ref_palette(ptimes, pals, seeds, tstart, tstep, rows=64):
 
 if __name__ == '__main__':
     print(build(force=True))
+
+
+class RefIterate(object):
+    """The reference's iterate-kernel text rendered for one of the sample genomes
+    (`tag` in ref_kernels.json['iterate']): apply_xf_<id>, the xform choice chain and
+    final xform + camera + trunca + bounds test, on arrays."""
+    def __init__(self, tag, ev):
+        """``ev``: oracle.flame_ref.GenomeEval of the same genome; the direct parameters
+        are read from its splines at the first temporal sample."""
+        import ctypes
+        import numpy as np
+        self.tag, self.L = tag, lib()
+        self.inputs = meta()['iterate'][tag]
+        vals = np.array([ev.spline(tuple(p.split('.')))[0] for p in self.inputs], np.float32)
+        d = ev.dim
+        getattr(self.L, 'ref_%s_setup' % tag)(_fp(vals), ctypes.c_int(d['w']), ctypes.c_int(d['aw']),
+                                              ctypes.c_int(d['ah']), ctypes.c_int(d['astride']))
+
+    def _arrays(self, xs, ys, cs, seeds):
+        import numpy as np
+        return (np.array(xs, np.float32), np.array(ys, np.float32), np.array(cs, np.float32),
+                np.array(seeds, np.uint32))
+
+    def apply(self, xf, xs, ys, cs, seeds):
+        """xf: index of the xform in sorted-key order, -1 for the final xform."""
+        import ctypes
+        xs, ys, cs, seeds = self._arrays(xs, ys, cs, seeds)
+        getattr(self.L, 'ref_%s_apply' % self.tag)(ctypes.c_int(xf), _fp(xs), _fp(ys), _fp(cs),
+                                                   _fp(seeds), ctypes.c_int(xs.size))
+        return xs, ys, cs, seeds
+
+    def choose(self, sel, xs, ys, cs, seeds):
+        import ctypes
+        import numpy as np
+        xs, ys, cs, seeds = self._arrays(xs, ys, cs, seeds)
+        last = np.zeros(xs.size, np.int32)
+        getattr(self.L, 'ref_%s_choose' % self.tag)(ctypes.c_float(sel), _fp(xs), _fp(ys), _fp(cs),
+                                                    _fp(seeds), _fp(last), ctypes.c_int(xs.size))
+        return last, xs, ys, cs, seeds
+
+    def bin(self, xs, ys, cs, seeds):
+        """(bin index or -1, colour after the final xform, seeds)."""
+        import ctypes
+        import numpy as np
+        xs, ys, cs, seeds = self._arrays(xs, ys, cs, seeds)
+        idx, cc = np.zeros(xs.size, np.int32), np.zeros(xs.size, np.float32)
+        getattr(self.L, 'ref_%s_bin' % self.tag)(_fp(xs), _fp(ys), _fp(cs), _fp(seeds), _fp(idx),
+                                                 _fp(cc), ctypes.c_int(xs.size))
+        return idx, cc, seeds
+
+
+def ref_ptx(name):
+    """Inline-PTX text of the reference: 'iter_accumulate', 'flush_atom', 'trunca'."""
+    return meta()['ptx'][name]

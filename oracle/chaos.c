@@ -61,7 +61,8 @@ void oracle_mwc_sums(uint32_t *seeds, int nstreams, int rounds, uint64_t *sums) 
 #define XF_VARS     16
 #define VAR_STRIDE  12   /* id, weight, 10 args */
 #define MAX_VARS    16
-#define XF_FLOATS   (XF_VARS + MAX_VARS * VAR_STRIDE)
+#define XF_OPACITY  (XF_VARS + MAX_VARS * VAR_STRIDE)   /* has_opacity, opacity */
+#define XF_FLOATS   (XF_OPACITY + 2)
 #define MAX_XF      64
 /* frame record: camera[6], density[MAX_XF], then (nxf + has_final) xforms */
 #define FR_CAM      0
@@ -662,11 +663,18 @@ static inline int bad_point(float x, float y) { return !isfinite(fabsf(x) + fabs
  * point, runs `fuse` unrecorded iterations, then its range.  Sample k uses
  * temporal sample (k * nts) / nsamples and palette row ts * pal_rows / nts.
  * hist is float4 [aheight][astride], accumulated with atomic float adds.
+ *
+ * xaos (NULL or float [nts][nxf][nxf-1]): cumulative densities of the next xform
+ * given the previous one (precalc_chaos, code/iter.py:32-54; the chain of
+ * iter.py:236-257); a trajectory starts with previous xform 0 (iter.py:209).
+ * An xform whose record carries an opacity draws its point with that probability
+ * (genome/specs.py:17); the point stays on the trajectory either way.
  */
-void oracle_iterate(const float *frames, int frame_stride, int nts, int nxf,
-                    int has_final, const float *palette, int pal_rows,
-                    float *hist, int astride, int aheight, uint32_t *seeds,
-                    int ntraj, uint64_t nsamples, int fuse, int nthreads) {
+void oracle_iterate_ex(const float *frames, int frame_stride, int nts, int nxf,
+                       int has_final, const float *palette, int pal_rows,
+                       float *hist, int astride, int aheight, uint32_t *seeds,
+                       int ntraj, uint64_t nsamples, int fuse, int nthreads,
+                       const float *xaos) {
     if (nthreads > 0) {
 #ifdef _OPENMP
         extern void omp_set_num_threads(int);
@@ -682,17 +690,26 @@ void oracle_iterate(const float *frames, int frame_stride, int nts, int nxf,
         mwc_t rng = {seeds[3 * j], seeds[3 * j + 1], seeds[3 * j + 2]};
         float color_dither = 0.49f * mwc_11(&rng);
         float x = mwc_11(&rng), y = mwc_11(&rng), c = mwc_01(&rng);
+        int last = 0;
         for (int64_t k = -(int64_t)fuse; k < (int64_t)(k1 - k0); k++) {
             uint64_t ks = k0 + (k < 0 ? 0 : (uint64_t)k);
             int ts = (int)((ks * (uint64_t)nts) / nsamples);
             const float *fr = frames + (size_t)ts * frame_stride;
             if (bad_point(x, y)) { x = mwc_11(&rng); y = mwc_11(&rng); c = mwc_01(&rng); }
             float sel = mwc_01(&rng);
+            const float *den = xaos ? xaos + ((size_t)ts * nxf + last) * (nxf - 1) : fr + FR_DEN;
             int pick = nxf - 1;
             for (int i = 0; i < nxf - 1; i++)
-                if (sel <= fr[FR_DEN + i]) { pick = i; break; }
-            apply_xform(fr + FR_XF + pick * XF_FLOATS, &x, &y, &c, &rng);
-            if (k < 0) continue;
+                if (sel <= den[i]) { pick = i; break; }
+            const float *xf = fr + FR_XF + pick * XF_FLOATS;
+            apply_xform(xf, &x, &y, &c, &rng);
+            last = pick;
+            int visible = 1;
+            if (xf[XF_OPACITY] != 0.0f) {
+                float op = xf[XF_OPACITY + 1];
+                visible = op >= 1.0f || mwc_01(&rng) < op;
+            }
+            if (k < 0 || !visible) continue;
 
             float fx = x, fy = y, fc = c;
             if (has_final) apply_xform(fr + FR_XF + nxf * XF_FLOATS, &fx, &fy, &fc, &rng);
@@ -714,4 +731,12 @@ void oracle_iterate(const float *frames, int frame_stride, int nts, int nxf,
         seeds[3 * j + 1] = rng.state;
         seeds[3 * j + 2] = rng.carry;
     }
+}
+
+void oracle_iterate(const float *frames, int frame_stride, int nts, int nxf,
+                    int has_final, const float *palette, int pal_rows,
+                    float *hist, int astride, int aheight, uint32_t *seeds,
+                    int ntraj, uint64_t nsamples, int fuse, int nthreads) {
+    oracle_iterate_ex(frames, frame_stride, nts, nxf, has_final, palette, pal_rows, hist,
+                      astride, aheight, seeds, ntraj, nsamples, fuse, nthreads, NULL);
 }

@@ -269,6 +269,7 @@ class GenomeEval(object):
         self.times = sample_times(ts, td / nts, nts)
         self.xform_ids = sorted(str(k) for k in gnm['xforms'])
         self.has_final = 'final_xform' in gnm
+        self.xaos = any('chaos' in gnm['xforms'][k] for k in gnm['xforms'])
         self.values = {}
         self._build()
 
@@ -306,6 +307,8 @@ class GenomeEval(object):
             self._affine(xpath + ('post_affine',))
         self._set(xpath + ('color',), self.spline(xpath + ('color',)))
         self._set(xpath + ('color_speed',), self.spline(xpath + ('color_speed',)))
+        if 'opacity' in xf:
+            self._set(xpath + ('opacity',), self.spline(xpath + ('opacity',)))
         for v in sorted(xf.get('variations', {})):
             vp = xpath + ('variations', v)
             self._set(vp + ('weight',), self.spline(vp + ('weight',)))
@@ -346,9 +349,24 @@ class GenomeEval(object):
                 total = total + w_
             rsum = f32(1.0) / total
             run = np.zeros(self.nts, f32)
-            for xid, w_ in list(zip(self.xform_ids, ws))[:-1]:
-                run = run + w_ * rsum
-                self._set(('xforms', xid, 'density'), run)
+            if not self.xaos:
+                for xid, w_ in list(zip(self.xform_ids, ws))[:-1]:
+                    run = run + w_ * rsum
+                    self._set(('xforms', xid, 'density'), run)
+            else:
+                # precalc_chaos (code/iter.py:32-54): per previous xform p, the cumulative
+                # normalised products weight[n] * chaos[p][n]
+                for pid in self.xform_ids:
+                    den = [w_ * self.spline(('xforms', pid, 'chaos', nid))
+                           for nid, w_ in zip(self.xform_ids, ws)]
+                    total = np.zeros(self.nts, f32)
+                    for d in den:
+                        total = total + d
+                    rsum = f32(1.0) / total
+                    run = np.zeros(self.nts, f32)
+                    for nid, d in list(zip(self.xform_ids, den))[:-1]:
+                        run = run + d * rsum
+                        self._set(('xforms', pid, 'chaos_den', nid), run)
         # camera (iter.py:56-79)
         rot = (self.spline(('camera', 'rotation')) * f32(3.14159274101257)) / f32(180.0)
         rs, rc = det_sincosf(rot)
@@ -396,6 +414,9 @@ class GenomeEval(object):
         if len(names) > 16:
             raise ValueError('oracle supports at most 16 variations per xform')
         rec[:, 15] = len(names)
+        if 'opacity' in xf:
+            rec[:, n - 2] = 1.0
+            rec[:, n - 1] = g('opacity')
         for vi, v in enumerate(names):
             base = 16 + vi * 12
             rec[:, base] = _VAR_NUM[v]
@@ -411,8 +432,9 @@ class GenomeEval(object):
         fr = np.zeros((self.nts, stride), f32)
         for i, c in enumerate(('xx', 'xy', 'xo', 'yx', 'yy', 'yo')):
             fr[:, i] = self.values['camera.' + c]
-        for i, xid in enumerate(self.xform_ids[:-1]):
-            fr[:, 6 + i] = self.values['xforms.%s.density' % xid]
+        if not self.xaos:
+            for i, xid in enumerate(self.xform_ids[:-1]):
+                fr[:, 6 + i] = self.values['xforms.%s.density' % xid]
         xfn = lib.oracle_xf_floats()
         off = 6 + 64
         for i, xid in enumerate(self.xform_ids):
@@ -551,10 +573,17 @@ def iterate(ev, palette, seeds, nsamples, ntraj=4096, fuse=32, nthreads=0):
     hist = np.zeros((dim['ah'], dim['astride'], 4), f32)
     seeds = np.ascontiguousarray(seeds, np.uint32).copy()
     pal = np.ascontiguousarray(palette, f32)
-    L.oracle_iterate(_p(fr), ctypes.c_int(fr.shape[1]), ctypes.c_int(ev.nts),
-                     ctypes.c_int(len(ev.xform_ids)), ctypes.c_int(1 if ev.has_final else 0),
-                     _p(pal), ctypes.c_int(pal.shape[0]), _p(hist),
-                     ctypes.c_int(dim['astride']), ctypes.c_int(dim['ah']), _p(seeds),
-                     ctypes.c_int(ntraj), ctypes.c_uint64(int(nsamples)),
-                     ctypes.c_int(fuse), ctypes.c_int(nthreads))
+    xaos = None
+    if ev.xaos and len(ev.xform_ids) > 1:
+        ids = ev.xform_ids
+        xaos = np.ascontiguousarray(np.stack(
+            [np.stack([ev.values['xforms.%s.chaos_den.%s' % (p, n)] for n in ids[:-1]], axis=1)
+             for p in ids], axis=1), f32)                     # [nts][nxf][nxf-1]
+    L.oracle_iterate_ex(_p(fr), ctypes.c_int(fr.shape[1]), ctypes.c_int(ev.nts),
+                        ctypes.c_int(len(ev.xform_ids)), ctypes.c_int(1 if ev.has_final else 0),
+                        _p(pal), ctypes.c_int(pal.shape[0]), _p(hist),
+                        ctypes.c_int(dim['astride']), ctypes.c_int(dim['ah']), _p(seeds),
+                        ctypes.c_int(ntraj), ctypes.c_uint64(int(nsamples)),
+                        ctypes.c_int(fuse), ctypes.c_int(nthreads),
+                        _p(xaos) if xaos is not None else None)
     return hist, seeds

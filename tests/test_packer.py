@@ -155,7 +155,7 @@ def test_reduction_placement_follows_the_genome_weight():
     from cuburn_b200.code import itergen
     heavy = {name: itergen.is_heavy(itergen.GenomePacker(make()))
              for name, make in samples.GENOMES.items()}
-    assert heavy == {'G3': False, 'G6F': True, 'G24H': True}
+    assert heavy == {'G3': False, 'G6F': True, 'G24H': True, 'G2M': False}
     for name, make in samples.GENOMES.items():
         src = itergen.generate_source(itergen.GenomePacker(make()), 1)
         assert ('#define RED_BEFORE_PULL %d' % heavy[name]) in src

@@ -148,7 +148,8 @@ def test_device_variation_vs_reference_code(native, built, name):
     c = ctypes
     mod.launch('cb_probe_xform', ((n + 255) // 256,), (256,),
                [c.c_uint64(d_par.ptr), c.c_uint64(d_x.ptr), c.c_uint64(d_y.ptr),
-                c.c_uint64(d_c.ptr), c.c_uint64(d_s.ptr), c.c_int(n), c.c_float(0.0), c.c_int(0)])
+                c.c_uint64(d_c.ptr), c.c_uint64(d_s.ptr), c.c_int(n), c.c_float(0.0), c.c_int(0),
+                c.c_int(0), c.c_uint64(0), c.c_uint64(0)])
     N.check(N.lib().cb_device_sync())
     gx, gy = N.from_device(d_x, (n,), np.float32), N.from_device(d_y, (n,), np.float32)
     gseeds = N.from_device(d_s, (n, 3), np.uint32)

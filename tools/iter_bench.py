@@ -37,7 +37,7 @@ for gname, w, h, spp in cases:
         names, hdrs = itergen.load_headers()
         mod = N.Module(src, 'iter.cu', hdrs, names, itergen.NVRTC_OPTIONS)
         rdr = render.Renderer(gnm, gprof)
-        rdr._variants[(still, False)] = mod
+        rdr._variants[(still, False, False)] = mod
         if not still:
             gprof2 = profile.wrap(dict(width=w, height=h, spp=spp, frame_width=float(os.environ.get('FW', 1e-9)), start=1, end=2), gnm)
         else:
