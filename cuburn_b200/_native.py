@@ -111,7 +111,7 @@ _SIGNATURES = {
     'cb_palette_pack': (c_int, [c_uint64, c_uint64, c_int, c_void_p]),
     'cb_flush_packed': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_hist_unswizzle': (c_int, [c_uint64, c_uint64, c_int, POINTER(Dims), c_void_p]),
-    'cb_hot_scan': (c_int, [c_uint64, c_uint64, c_uint64, c_uint64, c_int, c_float,
+    'cb_hot_scan': (c_int, [c_uint64, c_uint64, c_uint64, c_uint64, c_int, c_float, c_float,
                             POINTER(Dims), c_void_p]),
     'cb_yuv_to_rgb': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_den_blur': (c_int, [c_uint64, c_uint64, c_int, c_int, POINTER(c_float),

@@ -273,36 +273,61 @@ struct op_colorclip : op_base {
 // ---- hot-bin scan (iterate support) -------------------------------------------------
 // After a short pilot pass of the chaos game, find the bins that hold at least
 // `threshold` samples and enter them into the direct-mapped table the HOT_BINS variant
-// of the iterate kernel keeps in shared memory (device/iter_kernel.cuh).  Where two hot
-// bins hash to one slot the hotter one wins (atomicMax on density << 32 | bin); the
-// other stays on the global-reduction path.  The reference's counterpart is the hotspot
-// flag computation at the end of flush_atom (code/iter.py:481-526).
-#define HOT_SLOTS 512
-#define HOT_HASH_MUL 2654435761u
-#define HOT_HASH_SHIFT 23
+// of the iterate kernel keeps in shared memory (device/iter_kernel.cuh).  Eight hash
+// multipliers are tried at once; where two hot bins share a slot the hotter one wins
+// (atomicMax on density << 32 | bin) and the other stays on the global-reduction path;
+// the multiplier that places most bins is the one the frame uses.  `count` receives the
+// number of bins at or above `trigger` (>= threshold): the host switches the variant on
+// only when some bin is hot enough to be bound by single-address atomic throughput.
+// The reference's counterpart is the hotspot flag computation at the end of flush_atom
+// (code/iter.py:481-526).
+#define HOT_SLOTS 1024
+#define HOT_HASH_SHIFT 22
+#define HOT_TRIES 8
 #define HIST_SWZ_INV 30599u          // 40503 * 30599 = 1 (mod 65536)
+__constant__ unsigned int c_hot_muls[HOT_TRIES] = {
+    2654435761u, 2246822519u, 3266489917u, 668265263u,
+    374761393u, 1540483477u, 2891336453u, 4182319919u};
 
 __global__ void __launch_bounds__(256)
-k_hot_scan(unsigned long long *best, const float4 *hist, int nbins, int swizzle_bins,
-           float threshold) {
+k_hot_scan(unsigned long long *best, int *ntrigger, const float4 *hist, int nbins,
+           int swizzle_bins, float threshold, float trigger) {
     const int i = blockIdx.x * 256 + threadIdx.x;      // storage index
     if (i >= nbins) return;
     const float w = hist[i].w;
     if (w < threshold) return;
     unsigned int u = (unsigned int)i;
     if (i < swizzle_bins) u = (u & 0xffff0000u) | ((u * HIST_SWZ_INV) & 0xffffu);
-    const unsigned int slot = (u * HOT_HASH_MUL) >> HOT_HASH_SHIFT;
-    atomicMax(best + slot, ((unsigned long long)__float_as_uint(w) << 32) | u);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(w) << 32) | u;
+#pragma unroll
+    for (int t = 0; t < HOT_TRIES; t++)
+        atomicMax(best + t * HOT_SLOTS + ((u * c_hot_muls[t]) >> HOT_HASH_SHIFT), key);
+    if (w >= trigger) atomicAdd(ntrigger, 1);
 }
 
+// count[0] = bins >= trigger (accumulated by k_hot_scan in count[1]), count[1] reset
 __global__ void __launch_bounds__(HOT_SLOTS)
 k_hot_finish(int *tags, int *count, unsigned long long *best) {
+    __shared__ int placed[HOT_TRIES];
+    __shared__ int pick;
     const int s = threadIdx.x;
-    const unsigned long long b = best[s];
+    for (int t = 0; t < HOT_TRIES; t++) {
+        const int n = __syncthreads_count(best[t * HOT_SLOTS + s] != 0ull);
+        if (s == 0) placed[t] = n;
+    }
+    if (s == 0) {
+        int p = 0;
+        for (int t = 1; t < HOT_TRIES; t++) if (placed[t] > placed[p]) p = t;
+        pick = p;
+        tags[HOT_SLOTS] = (int)c_hot_muls[p];
+        count[0] = count[1];
+        count[1] = 0;
+        count[2] = placed[p];
+    }
+    __syncthreads();
+    const unsigned long long b = best[pick * HOT_SLOTS + s];
     tags[s] = b ? (int)(unsigned int)b : -1;
-    best[s] = 0ull;                                    // ready for the next frame
-    const int n = __syncthreads_count(b != 0ull);
-    if (s == 0) *count = n;
+    for (int t = 0; t < HOT_TRIES; t++) best[t * HOT_SLOTS + s] = 0ull;     // next frame
 }
 
 // ---- 7-tap directional blurs ----------------------------------------------------
@@ -350,73 +375,10 @@ k_full_blur(float4 *dst, const float4 *src, int pattern, int upsample, coefs7 k,
 }
 
 // ---- directional bilateral filter (code/filters.py:166-264) -------------------
-// Weighted mean of the 2*radius+1 taps along one direction.  Weight = spatial
-// term x colour-distance term x density-distance term x (for r != 0) a Gompertz
-// gradient term that pulls energy uphill.
-__global__ void __launch_bounds__(256)
-k_bilateral(float4 *dst, const float4 *src, const float *blur, int pattern,
-            int radius, float sstd, float cstd, float dstd, float dpow,
-            float gspeed, cb_dims dim) {
-    PIX_XY();
-    __shared__ float spa[32];
-    if (threadIdx.y == 0) {
-        float df = (float)threadIdx.x;
-        spa[threadIdx.x] = expf(df * df / (-K_SQRT2 * sstd));
-    }
-    const int W = dim.astride, H = dim.aheight;
-    const float cscale = 1.0f / (-K_SQRT2 * 3.0f * cstd);
-    const float dscale = -0.5f / dstd;
-
-    float4 cen = src[gi];
-    float cdrcp = 1.0f / (cen.w + 1.0e-6f);
-    cen.x *= cdrcp; cen.y *= cdrcp; cen.z *= cdrcp;
-    float cpowden = powf(cen.w, dpow);
-
-    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float wsum = 0.0f;
-    __syncthreads();
-
-    int2 o = shear_offset(pattern, (float)(-radius - 1));
-    float4 pix = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
-    o = shear_offset(pattern, (float)(-radius));
-    float4 next = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
-
-    for (int r = -radius; r <= radius; r++) {
-        float prev = pix.w;
-        pix = next;
-        o = shear_offset(pattern, (float)(r + 1));
-        next = src[clamp_idx(xi + o.x, yi + o.y, W, H)];
-
-        float cdiff = 0.5f;
-        if (pix.w > 0.0f && cen.w > 0.0f) {
-            float pdrcp = 1.0f / pix.w;
-            float yd = pix.x * pdrcp - cen.x;
-            float ud = pix.y * pdrcp - cen.y;
-            float vd = pix.z * pdrcp - cen.z;
-            cdiff = yd * yd + ud * ud + vd * vd;
-        }
-        float powden = powf(pix.w, dpow);
-        float dfact = exp2f(dscale * fabsf(cpowden - powden));
-
-        o = shear_offset(pattern, (float)r);
-        float avg = blur[clamp_idx(xi + o.x, yi + o.y, W, H)];
-        float grad = (next.w - prev) / (avg + 1.0e-6f);
-        if (r < 0) grad = -grad;
-        float gfact = exp2f(-exp2f(gspeed * grad));
-
-        float f = spa[abs(r)] * expf(cscale * cdiff) * dfact;
-        if (r != 0) f *= gfact;
-        wsum += f;
-        acc.x += f * pix.x;
-        acc.y += f * pix.y;
-        acc.z += f * pix.z;
-        acc.w += f * pix.w;
-    }
-    float rcp = 1.0f / (wsum + 1e-10f);
-    dst[gi] = make_float4(acc.x * rcp, acc.y * rcp, acc.z * rcp, acc.w * rcp);
-}
-
-// ---- restructured bilateral direction (same result, ~3x fewer SFU ops) -----------
+// Weighted mean of the 2*radius+1 taps along one direction.  Weight = spatial term x
+// colour-distance term x density-distance term x (for r != 0) a Gompertz gradient term
+// that pulls energy uphill.
+// ---- restructured evaluation (same result, ~3x fewer SFU ops) --------------------
 // The reference kernel spends ~8 MUFU operations per tap (powf of the tap density,
 // three exponentials, two reciprocals).  Everything that depends on one pixel only
 // is hoisted into two small prologue kernels, and the per-tap weight is evaluated
@@ -479,6 +441,14 @@ k_bilat_prep2(float2 *side, const float2 *aux, int pattern, coefs7 k, cb_dims di
         for (int i = 0; i < 7; i++) den += d[p][i] * k.c[i];
         side[yi * dim.astride + xi] = make_float2(1.0f / (den + 1.0e-6f), cp[p]);
     }
+}
+
+// The same per-pixel record from a two-octave blur plane the caller computed itself
+// (cb_den_blur + cb_den_blur_1c, the reference's launch sequence filters.py:80-92).
+__global__ void __launch_bounds__(256)
+k_bilat_side(float2 *side, const float4 *src, const float *blur, float dpow, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) side[i] = make_float2(1.0f / (blur[i] + 1.0e-6f), powf(src[i].w, dpow));
 }
 
 // RADIUS > 0: compile-time radius (the loop unrolls); RADIUS == 0: run-time radius.
@@ -990,14 +960,15 @@ int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream 
 }
 
 int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
-                int swizzle_bins, float threshold, const cb_dims *dim, cb_stream s) {
+                int swizzle_bins, float threshold, float trigger, const cb_dims *dim,
+                cb_stream s) {
     CHECK_DIM(dim);
     CB_REQUIRE(swizzle_bins >= 0 && swizzle_bins % 65536 == 0 && swizzle_bins <= nbins(dim),
                "swizzle_bins must be a multiple of 65536 inside the grid");
-    CB_REQUIRE(threshold >= 1.0f, "threshold below one sample");
+    CB_REQUIRE(threshold >= 1.0f && trigger >= threshold, "need 1 <= threshold <= trigger");
     k_hot_scan<<<(nbins(dim) + 255) / 256, 256, 0, cb_cs(s)>>>(
-        cb_ptr<unsigned long long>(scratch), cb_ptr<const float4>(hist4), nbins(dim),
-        swizzle_bins, threshold);
+        cb_ptr<unsigned long long>(scratch), cb_ptr<int>(count) + 1, cb_ptr<const float4>(hist4),
+        nbins(dim), swizzle_bins, threshold, trigger);
     CB_LAUNCH_CHECK();
     k_hot_finish<<<1, HOT_SLOTS, 0, cb_cs(s)>>>(cb_ptr<int>(tags), cb_ptr<int>(count),
                                                 cb_ptr<unsigned long long>(scratch));
@@ -1126,19 +1097,51 @@ int cb_full_blur(cb_dptr dst4, cb_dptr src4, int pattern, int upsample,
     return CB_OK;
 }
 
+// The 31-tap pass over (src, side): sliding-window kernel for the y-major directions,
+// one pixel per thread otherwise.
+static int bilateral_main(float4 *dst, const float4 *src, const float2 *side, int pattern,
+                          int radius, float sstd, float cstd, float dstd, float gspeed,
+                          const cb_dims *dim, cb_stream s) {
+    const int step = radius == 15 ? bilat_window_step(pattern) : 0;
+    if (step) {
+        const bilat_tab tab = make_bilat_tab(pattern, step, sstd, dim->astride);
+        bilat_consts kc;
+        kc.cscale2 = 1.44269502162933f / (-K_SQRT2 * 3.0f * cstd);
+        kc.dscale = -0.5f / dstd;
+        kc.gspeed = gspeed;
+        const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
+        if (step == 1)
+            k_bilateral_window<1><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(dst, src, side, tab, kc, *dim);
+        else
+            k_bilateral_window<4><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(dst, src, side, tab, kc, *dim);
+    } else if (radius == 15)  // the reference's fixed radius (cuburn/filters.py:59): unrolled
+        k_bilateral_fast<15><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+            dst, src, side, pattern, radius, sstd, cstd, dstd, gspeed, *dim);
+    else
+        k_bilateral_fast<0><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
+            dst, src, side, pattern, radius, sstd, cstd, dstd, gspeed, *dim);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// The reference's `bilateral` launch (cuburn/filters.py:86-94): the caller has already
+// blurred the density twice into blur1.  Scratch for the per-pixel records comes from
+// the stream-ordered allocator.
 int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern, int radius,
                  float sstd, float cstd, float dstd, float dpow, float gspeed,
                  const cb_dims *dim, cb_stream s) {
     CHECK_DIM(dim);
     CB_REQUIRE(pattern >= 0 && pattern < 16, "bad direction");
-    CB_REQUIRE(radius >= 0 && radius < 32, "radius must be below 32");
-    k_bilateral<<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
-        cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), cb_ptr<const float>(blur1),
-        pattern, radius, sstd, cstd, dstd, dpow, gspeed, *dim);
-    CB_LAUNCH_CHECK();
-    return CB_OK;
+    CB_REQUIRE(radius >= 0 && radius <= 16, "radius must be at most 16");
+    float2 *side = nullptr;
+    CB_CUDA(cudaMallocAsync((void **)&side, sizeof(float2) * (size_t)nbins(dim), cb_cs(s)));
+    k_bilat_side<<<(nbins(dim) + 255) / 256, 256, 0, cb_cs(s)>>>(
+        side, cb_ptr<const float4>(src4), cb_ptr<const float>(blur1), dpow, nbins(dim));
+    int rc = bilateral_main(cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern,
+                            radius, sstd, cstd, dstd, gspeed, dim, s);
+    cudaFreeAsync(side, cb_cs(s));
+    return rc;
 }
-
 
 // One direction of the bilateral filter = den_blur + den_blur_1c + bilateral of the
 // reference recipe (cuburn/filters.py:80-94) with the per-pixel terms hoisted;
@@ -1159,30 +1162,8 @@ int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4, int pat
     CB_LAUNCH_CHECK();
     k_bilat_prep2<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
     CB_LAUNCH_CHECK();
-    const int step = radius == 15 ? bilat_window_step(pattern) : 0;
-    if (step) {
-        const bilat_tab tab = make_bilat_tab(pattern, step, sstd, dim->astride);
-        bilat_consts kc;
-        kc.cscale2 = 1.44269502162933f / (-K_SQRT2 * 3.0f * cstd);
-        kc.dscale = -0.5f / dstd;
-        kc.gspeed = gspeed;
-        const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
-        if (step == 1)
-            k_bilateral_window<1><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(
-                cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, tab, kc, *dim);
-        else
-            k_bilateral_window<4><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(
-                cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, tab, kc, *dim);
-    } else if (radius == 15)  // the reference's fixed radius (cuburn/filters.py:59): unrolled
-        k_bilateral_fast<15><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
-            cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
-            cstd, dstd, gspeed, *dim);
-    else
-        k_bilateral_fast<0><<<grid2(dim), dim3(32, 8), 0, cb_cs(s)>>>(
-            cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern, radius, sstd,
-            cstd, dstd, gspeed, *dim);
-    CB_LAUNCH_CHECK();
-    return CB_OK;
+    return bilateral_main(cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern,
+                          radius, sstd, cstd, dstd, gspeed, dim, s);
 }
 
 }  // extern "C"

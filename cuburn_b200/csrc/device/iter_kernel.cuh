@@ -60,7 +60,7 @@ struct iter_args {
     unsigned long long total_samples;
     unsigned long long *cells;                 // ACC_PACKED: u64 [aheight][astride]
     const unsigned long long *palette_packed;  // ACC_PACKED / HOT_BINS: u64 [pal_rows][256]
-    const int *hot_tags;                       // HOT_BINS: int [HOT_SLOTS], bin or -1
+    const int *hot_tags;                       // HOT_BINS: int [HOT_SLOTS + 1]: bin or -1, then the hash multiplier
     int first_round;        // phase of the exchange permutation to start from
 };
 
@@ -73,10 +73,14 @@ struct iter_args {
 #ifndef HOT_BINS
 #define HOT_BINS 0
 #endif
-// Slots of the per-CTA hot-bin table: a direct-mapped hash of the bin index.
-#define HOT_SLOTS 512
-#define HOT_HASH_MUL 2654435761u
-#define HOT_HASH_SHIFT 23
+// Slots of the per-CTA hot-bin table: a direct-mapped multiplicative hash of the bin
+// index; cb_hot_scan picks, per frame, the multiplier (out of eight) that places most
+// hot bins and stores it behind the tags.
+#define HOT_SLOTS 1024
+#define HOT_HASH_SHIFT 22
+// 20 KB of cells and tags per CTA: six CTAs per SM instead of eight.  Flames with hot
+// bins are bound by atomics, not by issue slots (profiles/r02_hot_bins.md).
+#define HOT_MIN_CTAS 6
 // Units between two flushes of the table into the histogram: keeps the 32-bit level
 // sums of a cell (<= 255 x samples) and the float conversion of its count exact.
 #define HOT_FLUSH_UNITS 32
@@ -204,8 +208,8 @@ struct hot_table {
     unsigned int cell[HOT_SLOTS][4];        // count, sum Y, sum U, sum V of 8-bit levels
 };
 
-__device__ __forceinline__ unsigned int hot_slot(int bin) {
-    return ((unsigned int)bin * HOT_HASH_MUL) >> HOT_HASH_SHIFT;
+__device__ __forceinline__ unsigned int hot_slot(int bin, unsigned int mul) {
+    return ((unsigned int)bin * mul) >> HOT_HASH_SHIFT;
 }
 
 // Called by the whole CTA between two barriers.
@@ -292,6 +296,7 @@ struct iter_smem {
 #if HOT_BINS
     unsigned long long palp[256];       // the unit's palette row as packed 8-bit levels
     hot_table hot;
+    unsigned int hot_mul;
 #endif
 };
 
@@ -301,7 +306,7 @@ __device__ __forceinline__ void record_sample(const iter_args &a, iter_smem &sm,
     accumulate_packed(a.cells + bin, a.hist + bin, sm.pal[cidx], (word & 31u) == (unsigned int)lane);
 #else
 #if HOT_BINS
-    const unsigned int hs = hot_slot(bin);
+    const unsigned int hs = hot_slot(bin, sm.hot_mul);
     if (sm.hot.tag[hs] == bin) {
         const unsigned long long p = sm.palp[cidx];
         atomicAdd(&sm.hot.cell[hs][0], 1u);
@@ -315,7 +320,12 @@ __device__ __forceinline__ void record_sample(const iter_args &a, iter_smem &sm,
 #endif
 }
 
-extern "C" __global__ void __launch_bounds__(ITER_THREADS, ITER_MIN_CTAS)
+#if HOT_BINS
+#define ITER_CTAS_PER_SM HOT_MIN_CTAS
+#else
+#define ITER_CTAS_PER_SM ITER_MIN_CTAS
+#endif
+extern "C" __global__ void __launch_bounds__(ITER_THREADS, ITER_CTAS_PER_SM)
 cb_iter(const __grid_constant__ iter_args a) {
     __shared__ iter_smem sm;
     xchg_buf *xb = sm.xb;
@@ -347,6 +357,7 @@ cb_iter(const __grid_constant__ iter_args a) {
         sm.hot.tag[s] = a.hot_tags[s];
         sm.hot.cell[s][0] = 0u; sm.hot.cell[s][1] = 0u; sm.hot.cell[s][2] = 0u; sm.hot.cell[s][3] = 0u;
     }
+    if (tid == 0) sm.hot_mul = (unsigned int)a.hot_tags[HOT_SLOTS];
     int units_done = 0;
 #endif
 

@@ -1,15 +1,29 @@
 """
-Nodes / edges -> animations.
+Nodes and edges -> animation documents.
 
-Drop-in for the reference blender (cuburn/genome/blend.py): ``node_to_anim``,
-``edge_to_anim``, ``resolve``, ``apply_temporal_offset``, ``blend``,
-``merge_edits``, ``tospline``, ``merge_nodes``, ``blend_xform``,
-``padding_xform``, ``sort_xforms``.  A node fixes position and velocity of every
-spline at one instant; blending two nodes yields the ``[p0, v0, p1, v1, t, p, ...]``
-animation splines the renderer packs, with periodic parameters (angles) extended
-by whole turns so that the interpolated motion matches the end velocities
-(blend.py:167-191), missing xforms padded by identity-like xforms
-(blend.py:223-258) and xforms paired by the configured sort (blend.py:266-314).
+Same entry points as the reference blender (cuburn/genome/blend.py): ``node_to_anim``,
+``edge_to_anim``, ``resolve``, ``apply_temporal_offset``, ``blend``, ``merge_edits``,
+``tospline``, ``merge_nodes``, ``blend_xform``, ``padding_xform``, ``sort_xforms``.
+Written from the behaviour those functions have on documents -- pinned by sixteen
+documents produced by executing the reference's blender (tests/golden/blend_golden.json)
+and by tests/test_convert.py -- not from its text.
+
+Model.  A *node* fixes, for every animated parameter, a position and a velocity at one
+instant: a bare number ``p`` (velocity 0) or ``[p, v]``.  An *edge* adds knots
+``[t, value, ...]`` in between (t = 0 and t = 1 override the ends).  The blend of two
+nodes over ``duration`` is, per parameter, the animation spline
+
+    [p0, v0, p1, v1, t, value, ...]      (collapsed to [p0, p1] or p0 when nothing moves)
+
+which is what the renderer packs into knot rows.  Periodic parameters (angles) first
+move the far end by whole periods so that the interpolated motion is the one the end
+velocities describe.  Xforms are blended in pairs; one without a partner is blended
+with a stand-in that draws nothing new (``padding_xform``).
+
+The document walk is driven by the schema: ``_schema_walk`` visits the positions the
+schema (genome/specs.py) defines and hands each leaf to a rule chosen by the leaf's
+type, so documents may carry extra keys (ids, links, blend options) without those
+leaking into the animation.
 """
 from itertools import zip_longest
 
@@ -17,188 +31,222 @@ from . import spectypes, specs, variations
 from .use import Wrapper
 from .util import get, resolve_spec, flatten, unflatten
 
-
-def node_to_anim(gdb, node, half):
-    """A node looped onto itself (one full period, or half of it centred on t=0)."""
-    node = resolve(gdb, node)
-    osrc, odst = (-0.25, 0.25) if half else (0, 1)
-    src = apply_temporal_offset(node, osrc)
-    dst = apply_temporal_offset(node, odst)
-    edge = dict(blend=dict(duration=odst - osrc, xform_sort='natural'))
-    return blend(src, dst, edge)
+_ABSENT = object()
 
 
-def edge_to_anim(gdb, edge):
-    edge = resolve(gdb, edge)
-    src, osrc = _split_ref_id(edge['link']['src'])
-    dst, odst = _split_ref_id(edge['link']['dst'])
-    src = apply_temporal_offset(resolve(gdb, gdb.get(src)), osrc)
-    dst = apply_temporal_offset(resolve(gdb, gdb.get(dst)), odst)
-    return blend(src, dst, edge)
-
-
-def resolve(gdb, item):
-    """Merge an item with its chain of ``base`` documents (later overrides earlier;
-    on edges, spline and list values concatenate instead)."""
-    is_edge = item['type'] == 'edge'
-    spec = specs.toplevels[item['type']]
-
-    def chain(i):
-        if i.get('base') is not None:
-            return chain(gdb.get(i['base'])) + [i]
-        return [i]
-    items = [flatten(i) for i in chain(item)]
-    out = {}
-    for k in set(key for i in items for key in i):
-        sp = resolve_spec(spec, k.split('.'))
-        vs = [i[k] for i in items if k in i]
-        if is_edge and isinstance(sp, (spectypes.Spline, spectypes.List)):
-            merged = []
-            for v in vs:
-                merged += v
-            out[k] = merged
-        else:
-            out[k] = vs[-1]
-    return unflatten(out)
-
-
-def _split_ref_id(s):
-    parts = s.split('@')
-    if len(parts) == 1:
-        return parts[0], 0
-    return parts[0], float(parts[1])
-
-
-def apply_temporal_offset(node, offset=0):
-    """Advance every periodic ``[position, velocity]`` spline by offset x velocity."""
-    class _Offset(Wrapper):
-        def wrap_spline(self, path, spec, val):
-            if spec.period is not None and isinstance(val, list) and val[1]:
-                position, velocity = val
-                return [position + offset * velocity, velocity]
-            return val
-    wr = _Offset(node)
-    return wr.visit(wr)
-
-
-def blend(src, dst, edit=None):
+# ---- walking documents along the schema -------------------------------------------
+def _schema_walk(schema, docs, leaf):
     """
-    Blend two pre-merged nodes (and an optional pre-merged edge ``edit``) into an
-    animation document (blend.py:80-133).
+    Combine several parallel documents (``None`` where one has nothing) into one.
+    ``leaf(spec, values)`` produces the value at a schema leaf; dictionaries of the
+    schema are descended into for every key at least one document carries and the
+    schema knows; maps (tables keyed by the document, like ``xforms``) are left to the
+    caller and come out as ``None``.
     """
-    edit = edit or {}
-    opts = {}
-    for d in (src, dst, edit):
-        opts.update(d.get('blend', {}))
-    opts = Wrapper(opts, specs.blend)
-
-    blended = merge_nodes(specs.node, src, dst, edit, opts.duration)
-    pairs = sort_xforms(src.get('xforms', {}), dst.get('xforms', {}), opts.xform_sort,
-                        explicit=opts.xform_map)
-    blended['xforms'] = {}
-    for sxf_key, dxf_key in pairs:
-        bxf_key = (sxf_key or 'pad') + '_' + (dxf_key or 'pad')
-        xf_edits = merge_edits(specs.xform,
-                               get(edit, {}, 'xforms', 'src', sxf_key),
-                               get(edit, {}, 'xforms', 'dst', dxf_key))
-        # 'dup' pairs an xform with a copy of its partner whose weight fades in/out
-        if sxf_key == 'dup':
-            xf_edits.setdefault('weight', []).extend([0, 0])
-        if dxf_key == 'dup':
-            xf_edits.setdefault('weight', []).extend([1, 0])
-        blended['xforms'][bxf_key] = blend_xform(
-            src.get('xforms', {}).get(sxf_key), dst.get('xforms', {}).get(dxf_key),
-            xf_edits, opts.duration)
-
-    if 'final_xform' in src or 'final_xform' in dst:
-        blended['final_xform'] = blend_xform(src.get('final_xform'), dst.get('final_xform'),
-                                             edit.get('final_xform'), opts.duration, True)
-    blended['type'] = 'animation'
-    blended.setdefault('time', {})['duration'] = opts.duration
-    return blended
+    if isinstance(schema, spectypes.Map):
+        return None
+    if not isinstance(schema, dict):
+        return leaf(schema, docs)
+    docs = [d if d is not None else {} for d in docs]
+    keys = set()
+    for d in docs:
+        keys.update(d)
+    return {k: _schema_walk(schema[k], [d.get(k) for d in docs], leaf)
+            for k in keys if k in schema}
 
 
-def merge_edits(sv, av, bv):
-    """Merge two edit trees according to the spec ``sv``."""
-    if isinstance(sv, (dict, spectypes.Map)):
-        av, bv = av or {}, bv or {}
-
-        def sub(k):
-            return sv.type if isinstance(sv, spectypes.Map) else sv[k]
-        return dict((k, merge_edits(sub(k), av.get(k), bv.get(k)))
-                    for k in set(av) | set(bv))
-    if isinstance(sv, (spectypes.List, spectypes.Spline)):
-        return (av or []) + (bv or [])
-    return bv if bv is not None else av
-
-
+# ---- one parameter -----------------------------------------------------------------
 def split_node_val(spl, val):
-    """A node spline value -> (position, velocity)."""
+    """Node value -> (position, velocity); missing values sit at the schema default."""
     if val is None:
         return spl.default, 0
     if isinstance(val, (int, float)):
         return val, 0
-    return val
+    position, velocity = val
+    return position, velocity
+
+
+def _edge_knots(edit):
+    """Edge knots ``[t, value, ...]`` -> (value at 0 | None, value at 1 | None, the rest
+    as a flat list); knots whose value is ``None`` are deletions and vanish."""
+    at = {}
+    for t, value in zip(edit[::2], edit[1::2]):
+        at[t] = value
+    start, end = at.pop(0, None), at.pop(1, None)
+    inner = []
+    for t, value in at.items():
+        if value is not None:
+            inner.extend((t, value))
+    return start, end, inner
+
+
+def _unwind(period, p0, v0, p1, v1, duration, start, end):
+    """
+    Far end of a periodic parameter, moved by whole periods.  The mean of the two end
+    velocities says how many periods the parameter travels during the blend; the far
+    end keeps its phase and takes the number of turns nearest to that.  Edge knots at
+    the ends are then brought to the same branch.
+    """
+    turns = duration * (v0 + v1) / (2.0 * period)
+    direction = 1.0 if turns >= 0 else -1.0
+    phase = (float(p1 - p0) / period) % direction       # in [0, 1) or (-1, 0]
+    p1 = p0 + (round(turns - phase) + phase) * period
+    if start is not None:
+        p0 += round(float(start - p0) / period) * period
+    if end is not None:
+        p1 += round(float(end - p1) / period) * period
+    return p0, p1
 
 
 def tospline(spl, src, dst, edit, duration):
-    """Two node values and the edge's knots -> one animation spline value."""
-    sp, sv = split_node_val(spl, src)
-    dp, dv = split_node_val(spl, dst)
-    # variation parameters copy the other side instead of falling back to the
-    # default, which could make a variation explode mid-blend
+    """Two node values (+ the edge's knots) -> one animation spline value."""
+    p0, v0 = split_node_val(spl, src)
+    p1, v1 = split_node_val(spl, dst)
     if spl.var:
+        # a variation parameter missing on one side copies the other side: falling back
+        # to the default could push the variation through a singularity mid-blend
         if src is None:
-            sp = dp
+            p0 = p1
         if dst is None:
-            dp = sp
-
-    knots = dict(zip(edit[::2], edit[1::2])) if edit else {}
-    e0, e1 = knots.pop(0, None), knots.pop(1, None)
-    rest = []
-    for k, v in knots.items():
-        if v is not None:
-            rest += [k, v]
-
+            p1 = p0
+    start, end, inner = _edge_knots(edit) if edit else (None, None, [])
     if spl.period:
-        # periodic extension: pick the number of whole turns that best matches
-        # the mean end velocity (blend.py:167-184)
-        def sign(x):
-            return 1. if x >= 0 else -1.
-        movement = duration * (sv + dv) / (2.0 * spl.period)
-        angdiff = (float(dp - sp) / spl.period) % (sign(movement))
-        dp = sp + (round(movement - angdiff) + angdiff) * spl.period
-        if e0 is not None:
-            sp += round(float(e0 - sp) / spl.period) * spl.period
-        if e1 is not None:
-            dp += round(float(e1 - dp) / spl.period) * spl.period
-    if rest or sv or dv or e0 or e1:
-        return [sp, sv, dp, dv] + rest
-    if sp != dp:
-        return [sp, dp]
-    return sp
+        p0, p1 = _unwind(spl.period, p0, v0, p1, v1, duration, start, end)
+    if inner or v0 or v1 or start or end:
+        return [p0, v0, p1, v1] + inner
+    return p0 if p0 == p1 else [p0, p1]
 
 
+# ---- whole documents ---------------------------------------------------------------
 def merge_nodes(sp, src, dst, edit, duration):
-    if isinstance(sp, dict):
-        src, dst, edit = src or {}, dst or {}, edit or {}
-        return dict((k, merge_nodes(sp[k], src.get(k), dst.get(k), edit.get(k), duration))
-                    for k in set(src) | set(dst) | set(edit) if k in sp)
-    if isinstance(sp, spectypes.Map):
-        # maps (xform tables) are blended pairwise by the caller
+    """Blend ``src`` and ``dst`` (with the edge's ``edit``) wherever schema ``sp`` reaches."""
+    def leaf(spec, values):
+        s, d, e = values
+        if isinstance(spec, spectypes.Spline):
+            return tospline(spec, s, d, e, duration)
+        if isinstance(spec, spectypes.List):
+            if isinstance(spec.type, spectypes.Palette):
+                # palettes become keyframes at the two ends of the blend
+                s = [[0] + s] if s is not None else s
+                d = [[1] + d] if d is not None else d
+            return (s or []) + (d or []) + (e or [])
+        for v in (e, d, s):                 # scalars: the edge wins, then the far node
+            if v is not None:
+                return v
         return None
-    if isinstance(sp, spectypes.Spline):
-        return tospline(sp, src, dst, edit, duration)
-    if isinstance(sp, spectypes.List):
-        if isinstance(sp.type, spectypes.Palette):
-            if src is not None:
-                src = [[0] + src]
-            if dst is not None:
-                dst = [[1] + dst]
-        return (src or []) + (dst or []) + (edit or [])
-    return edit if edit is not None else dst if dst is not None else src
+    return _schema_walk(sp, [src, dst, edit], leaf)
 
 
+def merge_edits(sv, av, bv):
+    """Overlay two edit trees: knot lists concatenate, other values take the later one."""
+    def leaf(spec, values):
+        a, b = values
+        if isinstance(spec, (spectypes.List, spectypes.Spline)):
+            return (a or []) + (b or [])
+        return a if b is None else b
+
+    def walk(schema, a, b):
+        # unlike _schema_walk, edit trees keep keys the schema does not list and descend
+        # into maps (their entries all have the map's type)
+        if isinstance(schema, (dict, spectypes.Map)):
+            a, b = a or {}, b or {}
+            sub = (lambda k: schema.type) if isinstance(schema, spectypes.Map) else schema.__getitem__
+            return {k: walk(sub(k), a.get(k), b.get(k)) for k in set(a) | set(b)}
+        return leaf(schema, (a, b))
+    return walk(sv, av, bv)
+
+
+def resolve(gdb, item):
+    """
+    An item with its chain of ``base`` documents folded in, oldest first: a later
+    document overrides an earlier one -- except on edges, where knot lists and lists
+    accumulate along the chain.
+    """
+    lineage = [item]
+    while lineage[0].get('base') is not None:
+        lineage.insert(0, gdb.get(lineage[0]['base']))
+    schema = specs.toplevels[item['type']]
+    accumulate = item['type'] == 'edge'
+    merged = {}
+    for doc in lineage:
+        for path, value in flatten(doc).items():
+            kind = resolve_spec(schema, path.split('.'))
+            if accumulate and path in merged and \
+                    isinstance(kind, (spectypes.Spline, spectypes.List)):
+                merged[path] = merged[path] + value
+            elif accumulate and isinstance(kind, (spectypes.Spline, spectypes.List)):
+                merged[path] = list(value)
+            else:
+                merged[path] = value
+    return unflatten(merged)
+
+
+def apply_temporal_offset(node, offset=0):
+    """The node ``offset`` blend-durations later: periodic ``[position, velocity]``
+    values advance along their velocity, everything else stays."""
+    class Shifted(Wrapper):
+        def wrap_spline(self, path, spec, val):
+            moving = spec.period is not None and isinstance(val, list) and val[1]
+            return [val[0] + offset * val[1], val[1]] if moving else val
+    view = Shifted(node)
+    return view.visit(view)
+
+
+def _ref_and_offset(ref):
+    """'id@0.25' -> ('id', 0.25); a bare id has offset 0."""
+    ident, _, offset = ref.partition('@')
+    return ident, (float(offset) if offset else 0)
+
+
+def node_to_anim(gdb, node, half):
+    """A node blended with itself one period later (``half``: half a period, centred)."""
+    node = resolve(gdb, node)
+    t0, t1 = (-0.25, 0.25) if half else (0, 1)
+    loop = {'blend': {'duration': t1 - t0, 'xform_sort': 'natural'}}
+    return blend(apply_temporal_offset(node, t0), apply_temporal_offset(node, t1), loop)
+
+
+def edge_to_anim(gdb, edge):
+    edge = resolve(gdb, edge)
+    ends = []
+    for side in ('src', 'dst'):
+        ident, offset = _ref_and_offset(edge['link'][side])
+        ends.append(apply_temporal_offset(resolve(gdb, gdb.get(ident)), offset))
+    return blend(ends[0], ends[1], edge)
+
+
+def blend(src, dst, edit=None):
+    """Two resolved nodes (and the resolved edge between them) -> an animation."""
+    edit = edit or {}
+    options = {}
+    for doc in (src, dst, edit):
+        options.update(doc.get('blend', {}))
+    options = Wrapper(options, specs.blend)
+    duration = options.duration
+
+    anim = merge_nodes(specs.node, src, dst, edit, duration)
+    sxfs, dxfs = src.get('xforms', {}), dst.get('xforms', {})
+    anim['xforms'] = {}
+    for skey, dkey in sort_xforms(sxfs, dxfs, options.xform_sort, explicit=options.xform_map):
+        knots = merge_edits(specs.xform, get(edit, {}, 'xforms', 'src', skey),
+                            get(edit, {}, 'xforms', 'dst', dkey))
+        # 'dup': the partner is a copy of the xform on the other side whose weight
+        # fades in from (or out to) nothing
+        if skey == 'dup':
+            knots.setdefault('weight', []).extend([0, 0])
+        if dkey == 'dup':
+            knots.setdefault('weight', []).extend([1, 0])
+        name = '%s_%s' % (skey or 'pad', dkey or 'pad')
+        anim['xforms'][name] = blend_xform(sxfs.get(skey), dxfs.get(dkey), knots, duration)
+    if 'final_xform' in src or 'final_xform' in dst:
+        anim['final_xform'] = blend_xform(src.get('final_xform'), dst.get('final_xform'),
+                                          edit.get('final_xform'), duration, True)
+    anim['type'] = 'animation'
+    anim.setdefault('time', {})['duration'] = duration
+    return anim
+
+
+# ---- xforms --------------------------------------------------------------------------
 def blend_xform(sxf, dxf, edits, duration, isfinal=False):
     if sxf is None:
         sxf = padding_xform(dxf, isfinal)
@@ -207,84 +255,99 @@ def blend_xform(sxf, dxf, edits, duration, isfinal=False):
     return merge_nodes(specs.xform, sxf, dxf, edits, duration)
 
 
-# an xform using one of these is padded with the inverted identity
-hole_variations = ('spherical ngon julian juliascope polar '
-                   'wedge_sph wedge_julia bipolar').split()
-# identity functions at their default parameter values
-ident_variations = 'rectangles fan2 blob perspective super_shape'.split()
+# Variations with a hole at the origin: shrinking their weight to zero opens the hole
+# over the whole picture, so their stand-in is a point reflection instead.
+hole_variations = frozenset(('spherical', 'ngon', 'julian', 'juliascope', 'polar',
+                             'wedge_sph', 'wedge_julia', 'bipolar'))
+# Variations that are the identity at their default parameters: the stand-in keeps them
+# (at defaults) so that only their parameters, not their weights, move during the blend.
+ident_variations = frozenset(('rectangles', 'fan2', 'blob', 'perspective', 'super_shape'))
+
+
+def _is_flipped(xf, which):
+    return get(xf, 45, which, 'spread') > 90
 
 
 def padding_xform(xf, isfinal):
-    """The do-nothing partner an unmatched xform is blended with (blend.py:223-258)."""
-    vs = {}
-    out = {'variations': vs, 'pre_affine': {'angle': 45}}
+    """The stand-in an unpaired xform is blended with: an identity-like xform matching
+    the orientation of ``xf``'s affines; a final xform's stand-in also has no colour pull."""
+    pad = {'pre_affine': {'angle': 45}, 'variations': {}}
     if isfinal:
-        out.update(weight=0, color_speed=0)
-    if get(xf, 45, 'pre_affine', 'spread') > 90:
-        out['pre_affine'] = {'angle': 135, 'spread': 135}
-    if get(xf, 45, 'post_affine', 'spread') > 90:
-        out['post_affine'] = {'angle': 135, 'spread': 135}
-    for k in xf.get('variations', {}):
-        if k in hole_variations:
-            out['pre_affine']['angle'] += 180
-            vs.clear()
-            vs['linear'] = dict(weight=-1)
-            return out
-        if k in ident_variations:
-            vs[k] = dict((pk, pv.default) for pk, pv in variations.var_params[k].items())
-    if vs:
-        n = float(len(vs))
-        for k in vs:
-            vs[k]['weight'] = 1 / n
+        pad['weight'] = 0
+        pad['color_speed'] = 0
+    for which in ('pre_affine', 'post_affine'):
+        if _is_flipped(xf, which):
+            pad[which] = {'angle': 135, 'spread': 135}
+    used = list(xf.get('variations', {}))
+    for name in used:
+        if name in hole_variations:
+            pad['pre_affine']['angle'] += 180
+            pad['variations'] = {'linear': {'weight': -1}}
+            return pad
+        if name in ident_variations:
+            pad['variations'][name] = {p: sp.default
+                                       for p, sp in variations.var_params[name].items()}
+    kept = pad['variations']
+    if not kept:
+        kept['linear'] = {'weight': 1}
     else:
-        vs['linear'] = dict(weight=1)
-    return out
+        share = 1 / float(len(kept))
+        for params in kept.values():
+            params['weight'] = share
+    return pad
 
 
 def halfhearted_human_sort_key(key):
+    """Numeric keys in numeric order, then the others alphabetically."""
     try:
         return (0, int(key), '')
     except (TypeError, ValueError):
         return (1, 0, str(key))
 
 
+def _scalar(value):
+    return value[0] if isinstance(value, (list, tuple)) else value
+
+
 def sort_xforms(sxfs, dxfs, sortmethod, explicit=()):
-    """Yield (src key | None, dst key | None) pairs (blend.py:266-314)."""
-    fwd, rev = {}, {}
-    for sx, dx in explicit:
-        if sx not in ('pad', 'dup') and sx in fwd:
-            rev.pop(fwd.pop(sx, None), None)
-        if dx not in ('pad', 'dup') and dx in rev:
-            fwd.pop(rev.pop(dx, None), None)
-        fwd[sx] = dx
-        rev[dx] = sx
-    for sd in sorted(fwd.items(), key=lambda kv: (str(kv[0]), str(kv[1]))):
-        yield sd
+    """
+    Pair the xforms of two nodes: a list of ``(src key | None, dst key | None)``.
+    Explicit pairs come first (a later pair releases an earlier claim on either xform;
+    'pad' and 'dup' are not xforms and can repeat).  The rest pair up rank by rank
+    inside classes of equal orientation (pre and post affine flipped or not), ranked by
+    ``sortmethod``: 'weight', 'weightflip' (descending on the far side), 'color', or
+    key order.
+    """
+    by_src, by_dst = {}, {}
+    for skey, dkey in explicit:
+        if skey not in ('pad', 'dup') and skey in by_src:
+            by_dst.pop(by_src.pop(skey), None)
+        if dkey not in ('pad', 'dup') and dkey in by_dst:
+            by_src.pop(by_dst.pop(dkey), None)
+        by_src[skey], by_dst[dkey] = dkey, skey
+    pairs = sorted(by_src.items(), key=lambda p: (str(p[0]), str(p[1])))
 
-    # remaining xforms are matched within classes: (pre flipped?, post flipped?)
-    scl, dcl = {}, {}
-    for cl, xfs, taken in ((scl, sxfs, fwd), (dcl, dxfs, rev)):
-        for k, v in xfs.items():
-            if k in taken:
-                continue
-            xcl = (get(v, 45, 'pre_affine', 'spread') > 90,
-                   get(v, 45, 'post_affine', 'spread') > 90)
-            cl.setdefault(xcl, []).append(k)
+    if sortmethod in ('weight', 'weightflip'):
+        def rank(xfs):
+            return lambda k: _scalar(xfs[k].get('weight', 0))
+    elif sortmethod == 'color':
+        def rank(xfs):
+            return lambda k: _scalar(xfs[k].get('color', 0))
+    else:
+        def rank(xfs):
+            return halfhearted_human_sort_key
 
-    def _num(v):
-        return v[0] if isinstance(v, (list, tuple)) else v
-
-    def order(keys, dct):
-        if sortmethod in ('weight', 'weightflip'):
-            return sorted(keys, key=lambda k: _num(dct[k].get('weight', 0)))
-        if sortmethod == 'color':
-            return sorted(keys, key=lambda k: _num(dct[k].get('color', 0)))
-        return sorted(keys, key=halfhearted_human_sort_key)
-
-    for cl in sorted(set(scl) | set(dcl)):
-        ssort = order(scl.get(cl, []), sxfs)
-        dsort = order(dcl.get(cl, []), dxfs)
+    def classes(xfs, taken):
+        out = {}
+        for key, xf in xfs.items():
+            if key not in taken:
+                cls = (_is_flipped(xf, 'pre_affine'), _is_flipped(xf, 'post_affine'))
+                out.setdefault(cls, []).append(key)
+        return {cls: sorted(keys, key=rank(xfs)) for cls, keys in out.items()}
+    sclasses, dclasses = classes(sxfs, by_src), classes(dxfs, by_dst)
+    for cls in sorted(set(sclasses) | set(dclasses)):
+        near, far = sclasses.get(cls, []), dclasses.get(cls, [])
         if sortmethod == 'weightflip':
-            dsort = list(reversed(dsort))
-        for sd in zip_longest(ssort, dsort):
-            yield sd
+            far = far[::-1]
+        pairs.extend(zip_longest(near, far))
+    return pairs

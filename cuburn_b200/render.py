@@ -27,6 +27,10 @@ Dimensions = N.Dims
 # ranges handed to cb_iterate are aligned to this.
 UNIT_SAMPLES = 16384
 ITER_THREADS = 256
+# layout of RenderManager.d_hot (cb_hot_scan): scratch, tags, counters
+HOT_TAGS_OFF = 8 * 1024 * 8
+HOT_COUNT_OFF = HOT_TAGS_OFF + 1028 * 4
+HOT_BYTES = HOT_COUNT_OFF + 16
 
 
 class DurationEvent(N.Event):
@@ -279,9 +283,9 @@ class RenderManager(object):
         self.filt_evt = self.copy_evt = None
         import collections
         self._pinned = collections.deque(maxlen=4)
-        # hot-bin table: u64 scratch[512] | int32 tags[512] | int32 count
-        self.d_hot = N.DeviceBuffer(512 * 8 + 512 * 4 + 16)
-        N.fill32(self.d_hot, (512 * 8 + 512 * 4 + 16) // 4, 0)
+        # hot-bin table: u64 scratch[8][1024] | int32 tags[1024 + 1, padded] | int32 count[4]
+        self.d_hot = N.DeviceBuffer(HOT_BYTES)
+        N.fill32(self.d_hot, HOT_BYTES // 4, 0)
         self._hot_probe = None          # (event, pinned count, renderer) of the last scan
         # share of the frame's samples this manager renders (multi-GPU stills)
         self.sample_share = (rank, world)
@@ -381,15 +385,17 @@ class RenderManager(object):
             return 16 * nbins > 1.5 * self._l2_bytes
         return self.accumulate == 'packed'
 
-    # Bins that collect more than ``hot_share`` of the samples are bound by the rate of
-    # one histogram address (~6.5e8 reductions/s); the frame's first ``1/hot_pilot`` of
-    # samples is rendered as a pilot, cb_hot_scan lists such bins, and the rest of the
-    # frame runs the HOT_BINS variant, which accumulates them in shared memory.  'auto':
+    # A bin that collects more than ~0.4 % of the samples is bound by the rate of one
+    # histogram address (~6.5e8 reductions/s).  The frame's first ``1/hot_pilot`` of
+    # samples is rendered as a pilot; if cb_hot_scan finds a bin above ``hot_trigger``,
+    # the rest of the frame runs the HOT_BINS variant, which accumulates every bin above
+    # ``hot_share`` in shared memory (it costs ~6 % on flames without such bins).  'auto':
     # probe every genome once (one host sync on a renderer's first frame), afterwards
     # follow the previous frame's scan without synchronising.  False: never; True:
     # always run the pilot and the HOT_BINS variant.
     hot_bins = 'auto'
     hot_share = 1.0 / 2048
+    hot_trigger = 1.0 / 512
     hot_pilot = 64
     hot_min_waves = 4               # frames shorter than this many waves of units: never
 
@@ -403,9 +409,13 @@ class RenderManager(object):
             fuse_rounds=fuse, first_sample=first, nsamples=n, total_samples=total,
             cells=self.fb.d_left.ptr if packed else 0,
             palette_packed=info.d_palette_packed.ptr,
-            hot_tags=self.d_hot.ptr + 512 * 8 if hot else 0, first_round=first_round)
+            hot_tags=self.d_hot.ptr + HOT_TAGS_OFF if hot else 0, first_round=first_round)
         N.check(N.lib().cb_iterate(mod.handle, N.byref(args),
-                                   rdr.grid_ctas(self.fb.nstreams, mod), s.handle))
+                                   self.iter_grid or rdr.grid_ctas(self.fb.nstreams, mod),
+                                   s.handle))
+
+    # persistent CTAs per cb_iterate launch; None: fill the GPU at the module's occupancy
+    iter_grid = None
 
     def _hot_decision(self, rdr, nunits, packed, grid):
         """(run the pilot + scan?, use the HOT_BINS variant?) for this frame."""
@@ -437,7 +447,7 @@ class RenderManager(object):
         still = gprof.frame_width(tc) == 0
         nunits = (n + UNIT_SAMPLES - 1) // UNIT_SAMPLES
         mod = rdr.variant(still, packed)
-        grid = rdr.grid_ctas(self.fb.nstreams, mod)
+        grid = self.iter_grid or rdr.grid_ctas(self.fb.nstreams, mod)
         pilot, hot = self._hot_decision(rdr, nunits, packed, grid)
         if still:
             mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
@@ -448,12 +458,12 @@ class RenderManager(object):
             npilot = grid * max(1, round(nunits / float(self.hot_pilot * grid))) * UNIT_SAMPLES
             self._launch_iter(mod, rdr, info, d_acc, swz, dim, first, npilot, total, fuse,
                               packed, False, s)
-            d_tags, d_count = self.d_hot.ptr + 512 * 8, self.d_hot.ptr + 512 * 8 + 512 * 4
-            N.check(N.lib().cb_hot_scan(d_tags, d_count, self.d_hot.ptr, int(d_acc), swz,
-                                        np.float32(max(32.0, self.hot_share * npilot)),
-                                        N.byref(dim), s.handle))
+            N.check(N.lib().cb_hot_scan(
+                self.d_hot.ptr + HOT_TAGS_OFF, self.d_hot.ptr + HOT_COUNT_OFF, self.d_hot.ptr,
+                int(d_acc), swz, np.float32(max(32.0, self.hot_share * npilot)),
+                np.float32(max(32.0, self.hot_trigger * npilot)), N.byref(dim), s.handle))
             count = self.fb.pool.allocate((1,), 'i4')
-            N.memcpy_dtoh(count, N.DeviceSlice(self.d_hot, 512 * 8 + 512 * 4, 4), s)
+            N.memcpy_dtoh(count, N.DeviceSlice(self.d_hot, HOT_COUNT_OFF, 4), s)
             evt = N.Event().record(s)
             self._hot_probe = (evt, count, rdr)
             self._pinned.append((count,))

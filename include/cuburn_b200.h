@@ -159,7 +159,7 @@ typedef struct {
                                 cells (count:10 | Y:18 | U:18 | V:18, iter.py:334-407) */
     cb_dptr palette_packed;  /* packed-accumulator and hot-bin modules: u64 [pal_rows][256]
                                 from cb_palette_pack */
-    cb_dptr hot_tags;        /* hot-bin module only: int32 [512] from cb_hot_scan */
+    cb_dptr hot_tags;        /* hot-bin module only: int32 [1025] from cb_hot_scan */
     int32_t first_round;     /* rounds every CTA has run in earlier calls of this frame
                                 (fuse rounds included): a frame split over several calls
                                 then draws the same samples as one call would */
@@ -183,12 +183,15 @@ int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream 
  * by flush_atom, iter.py:481-526, consumed at iter.py:319-329).  Here: after a short
  * pilot pass of cb_iterate, cb_hot_scan enters every bin of `hist4` (layout as
  * accumulated: swizzle_bins as in cb_iter_args) holding >= threshold samples into a
- * 512-slot table `tags` (bin index or -1; the hotter bin wins a shared slot) and writes
- * the number of entries to `count`; `scratch` is 512 zeroed u64 (left zeroed).  The
- * HOT_BINS variant of the iterate module accumulates those bins in shared memory as
- * integer level sums and folds them into the histogram itself. */
+ * 1024-slot hash table: `tags` = int32 [1025], bin index or -1 per slot (the hotter bin
+ * wins a shared slot), then the hash multiplier chosen for this frame.  `count` = int32
+ * [4] (zeroed once): count[0] receives the number of bins holding >= trigger samples,
+ * count[2] the number of table entries.  `scratch` = 8 x 1024 zeroed u64 (left zeroed).
+ * The HOT_BINS variant of the iterate module accumulates the listed bins in shared
+ * memory as integer level sums and folds them into the histogram itself. */
 int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
-                int swizzle_bins, float threshold, const cb_dims *dim, cb_stream s);
+                int swizzle_bins, float threshold, float trigger, const cb_dims *dim,
+                cb_stream s);
 
 /* Undo the accumulation layout: dst[i] = src[swizzle(i)] for i < swizzle_bins,
  * dst[i] = src[i] above; dst is the linear float4 [aheight][astride] histogram the
@@ -204,6 +207,10 @@ int cb_den_blur_1c(cb_dptr dst1, cb_dptr src1, int pattern, int upsample,
                    const float coefs[7], const cb_dims *dim, cb_stream s);
 int cb_full_blur(cb_dptr dst4, cb_dptr src4, int pattern, int upsample,
                  const float coefs[7], const cb_dims *dim, cb_stream s);
+/* The reference's `bilateral` launch (cuburn/filters.py:86-94, code/filters.py:166-264):
+ * blur1 is the density plane after cb_den_blur + cb_den_blur_1c(upsample 1).  Runs the
+ * same restructured 31-tap kernels as cb_bilateral_direction; the per-pixel records
+ * (8 bytes per bin) live in stream-ordered scratch memory for the duration of the call. */
 int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern,
                  int radius, float sstd, float cstd, float dstd, float dpow,
                  float gspeed, const cb_dims *dim, cb_stream s);
