@@ -72,11 +72,14 @@ _SIGNATURES = {
                                POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t)]),
     'cb_init': (c_int, [c_int]),
     'cb_device_sync': (c_int, []),
+    'cb_launch_count': (c_int, [POINTER(c_uint64)]),
     'cb_calc_dim': (c_int, [c_int, c_int, POINTER(Dims)]),
     'cb_malloc': (c_int, [c_size_t, POINTER(c_uint64)]),
     'cb_free': (c_int, [c_uint64]),
     'cb_host_alloc': (c_int, [c_size_t, POINTER(c_void_p)]),
     'cb_host_free': (c_int, [c_void_p]),
+    'cb_host_register': (c_int, [c_void_p, c_size_t]),
+    'cb_host_unregister': (c_int, [c_void_p]),
     'cb_stream_create': (c_int, [POINTER(c_void_p)]),
     'cb_stream_destroy': (c_int, [c_void_p]),
     'cb_stream_sync': (c_int, [c_void_p]),
@@ -138,6 +141,8 @@ _SIGNATURES = {
     'cb_logencode': (c_int, [c_uint64, c_uint64, c_float, POINTER(Dims), c_void_p]),
     'cb_convert': (c_int, [c_int, c_uint64, c_uint64, c_int, POINTER(Dims), c_uint64,
                            c_int, c_void_p]),
+    'cb_convert_rows': (c_int, [c_int, c_uint64, c_uint64, c_int, POINTER(Dims), c_uint64,
+                                c_int, c_int, c_int, c_void_p]),
     'cb_convert_size': (c_int, [c_int, POINTER(Dims), POINTER(c_size_t)]),
     'cb_comm_version': (c_int, [POINTER(c_int)]),
     'cb_comm_unique_id': (c_int, [POINTER(ctypes.c_uint8)]),
@@ -460,6 +465,13 @@ def device_info(device=0):
                                byref(mem), byref(l2)))
     return dict(name=name.value.decode(), cc=(maj.value, mnr.value), sm_count=sms.value,
                 total_mem=mem.value, l2_bytes=l2.value)
+
+
+def launch_count():
+    """Kernels launched by the library so far in this process."""
+    n = c_uint64()
+    check(lib().cb_launch_count(byref(n)))
+    return n.value
 
 
 def device_count():

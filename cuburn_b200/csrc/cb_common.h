@@ -29,8 +29,12 @@ void cb_set_error(const char *fmt, ...);
         }                                                                     \
     } while (0)
 
+// kernels of this library launched so far (cb_launch_count)
+extern unsigned long long g_cb_launches;
+
 #define CB_LAUNCH_CHECK()                                                     \
     do {                                                                      \
+        g_cb_launches++;                                                      \
         cudaError_t err__ = cudaGetLastError();                               \
         if (err__ != cudaSuccess) {                                           \
             cb_set_error("kernel launch failed: %s (%s:%d)",                  \

@@ -19,6 +19,8 @@ void cb_set_error(const char *fmt, ...) {
 
 int cb_sm_count() { return g_sm_count; }
 
+unsigned long long g_cb_launches = 0;
+
 extern "C" {
 
 const char *cb_last_error(void) { return g_err; }
@@ -99,6 +101,23 @@ int cb_host_alloc(size_t bytes, void **out) {
 
 int cb_host_free(void *p) {
     if (p) CB_CUDA(cudaFreeHost(p));
+    return CB_OK;
+}
+
+int cb_launch_count(uint64_t *count) {
+    CB_REQUIRE(count, "null argument");
+    *count = g_cb_launches;
+    return CB_OK;
+}
+
+int cb_host_register(void *p, size_t bytes) {
+    CB_REQUIRE(p && bytes, "null argument");
+    CB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return CB_OK;
+}
+
+int cb_host_unregister(void *p) {
+    if (p) CB_CUDA(cudaHostUnregister(p));
     return CB_OK;
 }
 

@@ -1137,6 +1137,7 @@ int cb_bilateral(cb_dptr dst4, cb_dptr src4, cb_dptr blur1, int pattern, int rad
     CB_CUDA(cudaMallocAsync((void **)&side, sizeof(float2) * (size_t)nbins(dim), cb_cs(s)));
     k_bilat_side<<<(nbins(dim) + 255) / 256, 256, 0, cb_cs(s)>>>(
         side, cb_ptr<const float4>(src4), cb_ptr<const float>(blur1), dpow, nbins(dim));
+    g_cb_launches++;
     int rc = bilateral_main(cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern,
                             radius, sstd, cstd, dstd, gspeed, dim, s);
     cudaFreeAsync(side, cb_cs(s));

@@ -197,6 +197,7 @@ int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,
                                       dyn_smem));
     CB_DRV(g_drv.LaunchKernel(f, gx, gy, gz, bx, by, bz, dyn_smem,
                               (CUstream)cb_cs(s), args, nullptr));
+    g_cb_launches++;
     return CB_OK;
 }
 

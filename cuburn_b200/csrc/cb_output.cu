@@ -34,10 +34,14 @@ __device__ __forceinline__ float jpeg_cr(float4 p) {
 
 #define CV_BATCH 4
 
+// Rows [row0, row1) of the output are converted; for the pixels of other rows a stream
+// only draws the random numbers it would have used (RGBA formats: four per pixel), so
+// that a frame converted band by band -- on one GPU or one band per GPU -- is identical
+// to the frame converted at once, and leaves the same RNG state behind.
 template <int FMT>
 __global__ void __launch_bounds__(256)
 k_convert(void *dstv, const float4 *src, int gutter, cb_dims dim, mwc_st *seeds,
-          int nstreams) {
+          int nstreams, int row0, int row1) {
     int sid = blockIdx.x * blockDim.x + threadIdx.x;
     if (sid >= nstreams) return;
     mwc_st rng = seeds[sid];
@@ -53,7 +57,8 @@ k_convert(void *dstv, const float4 *src, int gutter, cb_dims dim, mwc_st *seeds,
           int i = i0 + k * nstreams;
           if (i < npix) {
               int y = i / w, x = i - y * w;
-              batch[k] = src[(y + gutter) * dim.astride + x + gutter];
+              if (y >= row0 && y < row1)
+                  batch[k] = src[(y + gutter) * dim.astride + x + gutter];
           }
       }
 #pragma unroll
@@ -61,6 +66,10 @@ k_convert(void *dstv, const float4 *src, int gutter, cb_dims dim, mwc_st *seeds,
         int i = i0 + k * nstreams;
         if (i >= npix) break;
         int y = i / w, x = i - y * w;
+        if (y < row0 || y >= row1) {        // only reachable for the RGBA formats
+            mwc_next(rng); mwc_next(rng); mwc_next(rng); mwc_next(rng);
+            continue;
+        }
         float4 p = batch[k];
         if (FMT == CB_FMT_RGBA_U8) {
             uchar4 o;
@@ -139,9 +148,14 @@ int cb_convert_size(cb_pixfmt fmt, const cb_dims *dim, size_t *bytes) {
     return CB_OK;
 }
 
-int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
-               const cb_dims *dim, cb_dptr seeds, int nstreams, cb_stream s) {
+int cb_convert_rows(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
+                    const cb_dims *dim, cb_dptr seeds, int nstreams, int row0, int row1,
+                    cb_stream s) {
     CB_REQUIRE(dim && nstreams > 0, "bad convert arguments");
+    CB_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= dim->height, "rows outside the frame");
+    CB_REQUIRE((row0 == 0 && row1 == dim->height) ||
+               fmt == CB_FMT_RGBA_U8 || fmt == CB_FMT_RGBA_U16,
+               "row bands are supported for the RGBA formats");
     if (fmt == CB_FMT_YUV420P10)
         CB_REQUIRE(dim->width % 4 == 0 && dim->height % 2 == 0,
                    "yuv420p10 needs width % 4 == 0 and even height");
@@ -149,7 +163,7 @@ int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
     void *d = cb_ptr<void>(dst);
     const float4 *sp = cb_ptr<const float4>(src);
     mwc_st *sd = cb_ptr<mwc_st>(seeds);
-#define GO(F) k_convert<F><<<grid, 256, 0, cb_cs(s)>>>(d, sp, gutter, *dim, sd, nstreams)
+#define GO(F) k_convert<F><<<grid, 256, 0, cb_cs(s)>>>(d, sp, gutter, *dim, sd, nstreams, row0, row1)
     switch (fmt) {
     case CB_FMT_RGBA_U8: GO(CB_FMT_RGBA_U8); break;
     case CB_FMT_RGBA_U16: GO(CB_FMT_RGBA_U16); break;
@@ -162,6 +176,12 @@ int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
 #undef GO
     CB_LAUNCH_CHECK();
     return CB_OK;
+}
+
+int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
+               const cb_dims *dim, cb_dptr seeds, int nstreams, cb_stream s) {
+    CB_REQUIRE(dim, "bad convert arguments");
+    return cb_convert_rows(fmt, dst, src, gutter, dim, seeds, nstreams, 0, dim->height, s);
 }
 
 }  // extern "C"

@@ -212,10 +212,16 @@ class BandFilter(object):
     Rows inside the halo are wrong near the band's artificial edges and are never
     used; the band itself is bit-identical to the single-GPU result.
     """
-    def __init__(self, rank, world, root=0, comm=True):
+    def __init__(self, rank, world, root=0, comm=True, shared=None):
         """comm: True = torch.distributed gather, a NativeComm = cb_band_gather through
-        the C ABI, False = no exchange (one process playing a rank, for tests)."""
+        the C ABI, False = no exchange (one process playing a rank, for tests).
+        shared: a SharedFrame -- then nothing is gathered on the device: every GPU
+        converts its own band (Output.convert(rows=...)) and copies it to its place in
+        the shared host frame over its own PCIe link (RenderManager.queue_frame)."""
         self.rank, self.world, self.root, self.comm = rank, world, root, comm
+        self.shared = shared
+        if shared is not None:
+            self.comm = comm = False
         if comm is True:
             import torch
             import torch.distributed as dist
@@ -261,6 +267,57 @@ class BandFilter(object):
     def mean_gather_ms(self, last=None):
         evs = self._events[-last:] if last else self._events
         return float(np.mean([_elapsed(a, b) for a, b in evs])) if evs else None
+
+    def output_rows(self, dim, gutter=12):
+        """Rows of the cropped output frame that this rank's band covers."""
+        row0, row1 = band_rows(dim.ah, self.rank, self.world)
+        if self.rank == 0:
+            row0 = 0
+        if self.rank == self.world - 1:
+            row1 = dim.ah
+        return min(max(row0 - gutter, 0), dim.h), min(max(row1 - gutter, 0), dim.h)
+
+
+class SharedFrame(object):
+    """
+    One host frame in POSIX shared memory, mapped and page-locked by every process of the
+    job: each GPU copies the rows it produced straight into it.  Rank 0 creates the
+    segment; the name is derived from the rendezvous port so no exchange is needed
+    beyond a barrier.
+    """
+    _seq = 0
+
+    def __init__(self, shape, dtype, rank, world, barrier=None):
+        import mmap
+        import os
+        from . import _native as N
+        SharedFrame._seq += 1
+        self.rank = rank
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.path = '/dev/shm/cuburn_b200_%s_%d' % (os.environ.get('MASTER_PORT', str(os.getppid())),
+                                                    SharedFrame._seq)
+        if rank == 0:
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if barrier is not None:
+            barrier()
+        if rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        self.array = np.frombuffer(self._mm, dtype).reshape(shape)
+        N.check(N.lib().cb_host_register(self.array.ctypes.data, self.nbytes))
+        if barrier is not None:
+            barrier()
+        if rank == 0:
+            os.unlink(self.path)            # the mappings keep the segment alive
+
+    def close(self):
+        from . import _native as N
+        if self.array is not None:
+            N.check(N.lib().cb_host_unregister(self.array.ctypes.data))
+            self.array = None
+            self._mm.close()
 
 
 def gather_host_bands(frame, rank, world, root=0):

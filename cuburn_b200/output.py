@@ -28,10 +28,13 @@ def _h(stream):
     return stream.handle if stream is not None else None
 
 
-def launchC(fmt, dim, fb, stream):
-    """Convert fb.d_front -> fb.d_back (output.py:21-26)."""
-    N.check(N.lib().cb_convert(fmt, fb.d_back.ptr, fb.d_front.ptr, fb.gutter,
-                               N.byref(dim), fb.d_seeds.ptr, fb.nstreams, _h(stream)))
+def launchC(fmt, dim, fb, stream, rows=None):
+    """Convert fb.d_front -> fb.d_back (output.py:21-26); ``rows = (row0, row1)``
+    restricts it to those output rows (multi-GPU stills: one band per GPU)."""
+    row0, row1 = rows if rows is not None else (0, dim.h)
+    N.check(N.lib().cb_convert_rows(fmt, fb.d_back.ptr, fb.d_front.ptr, fb.gutter,
+                                    N.byref(dim), fb.d_seeds.ptr, fb.nstreams,
+                                    int(row0), int(row1), _h(stream)))
 
 
 class Output(object):
@@ -41,12 +44,22 @@ class Output(object):
     def shape(self, dim):
         raise NotImplementedError()
 
-    def convert(self, fb, gnm, dim, stream=None):
-        launchC(self.fmt, dim, fb, stream)
+    def convert(self, fb, gnm, dim, stream=None, rows=None):
+        launchC(self.fmt, dim, fb, stream, rows)
 
-    def copy(self, fb, dim, pool, stream=None):
-        h_out = pool.allocate(self.shape(dim), self.dtype)
-        N.memcpy_dtoh(h_out, fb.d_back, stream)
+    def copy(self, fb, dim, pool, stream=None, rows=None, out=None):
+        """Schedule the D2H copy of the converted frame (or of its ``rows``) into pinned
+        memory: a fresh array from ``pool``, or ``out`` -- e.g. a frame in shared memory
+        that every GPU of a banded still copies its own rows into."""
+        h_out = out if out is not None else pool.allocate(self.shape(dim), self.dtype)
+        if rows is None:
+            N.memcpy_dtoh(h_out, fb.d_back, stream)
+            return h_out
+        row0, row1 = rows
+        if row1 > row0:
+            band = h_out[row0:row1]                 # (h, w, 4) formats: rows are contiguous
+            off = row0 * band.strides[0]
+            N.memcpy_dtoh(band, N.DeviceSlice(fb.d_back, off, band.nbytes), stream)
         return h_out
 
     def encode(self, host_frame):
@@ -318,9 +331,9 @@ class VPxOutput(Output):
             return (dim.h * dim.w * 6 // 4,)
         return (3, dim.h, dim.w)
 
-    def convert(self, fb, gnm, dim, stream=None):
+    def convert(self, fb, gnm, dim, stream=None, rows=None):
         self.dim = dim
-        launchC(self.fmt, dim, fb, stream)
+        launchC(self.fmt, dim, fb, stream, rows)
 
     def _spawn(self, w, h):
         extras = ['-w', w, '-h', h]
@@ -370,9 +383,9 @@ class ProResOutput(Output):
     def shape(self, dim):
         return (3, dim.h, dim.w)
 
-    def convert(self, fb, gnm, dim, stream=None):
+    def convert(self, fb, gnm, dim, stream=None, rows=None):
         self.dim = dim
-        launchC(self.fmt, dim, fb, stream)
+        launchC(self.fmt, dim, fb, stream, rows)
 
     def encode(self, buf):
         if buf is None:

@@ -550,9 +550,14 @@ class RenderManager(object):
         if self.copy_evt:
             self.stream_a.wait_for_event(self.copy_evt)
         self._filter(rdr, gprof, dim, tc)
-        rdr.out.convert(self.fb, gprof, dim, self.stream_a)
+        rows = out = None
+        if self.band_filter is not None and getattr(self.band_filter, 'shared', None) is not None:
+            # a still sharded by rows: this GPU converts and copies out its own band
+            rows, out = self.band_filter.output_rows(dim, self.fb.gutter), \
+                self.band_filter.shared.array
+        rdr.out.convert(self.fb, gprof, dim, self.stream_a, rows=rows)
         self.filt_evt = N.Event().record(self.stream_a)
-        h_out = rdr.out.copy(self.fb, dim, self.fb.pool, self.stream_a)
+        h_out = rdr.out.copy(self.fb, dim, self.fb.pool, self.stream_a, rows=rows, out=out)
         self.copy_evt = DurationEvent(timing_event).record(self.stream_a)
 
         self.info_a, self.info_b = self.info_b, self.info_a

@@ -59,6 +59,9 @@ int cb_device_info(int device, char *name, size_t name_len, int *cc_major,
                    size_t *l2_bytes);
 int cb_init(int device);                                  /* main.py:38-41 */
 int cb_device_sync(void);
+/* Number of kernels this library has launched in this process (its own kernels and the
+ * NVRTC-built ones; memsets, copies and NCCL collectives are not counted). */
+int cb_launch_count(uint64_t *count);
 int cb_calc_dim(int width, int height, cb_dims *out);     /* render.py:80-89 */
 
 /* ---- memory, streams, events (PyCUDA driver calls, SURVEY 8b index) ------- */
@@ -66,6 +69,10 @@ int cb_malloc(size_t bytes, cb_dptr *out);                /* render.py:133-138 *
 int cb_free(cb_dptr p);
 int cb_host_alloc(size_t bytes, void **out);              /* pinned; render.py:93 */
 int cb_host_free(void *p);
+/* Page-lock memory the caller owns (e.g. a shared-memory frame several GPU processes
+ * copy their bands into) so that device->host copies into it are asynchronous. */
+int cb_host_register(void *p, size_t bytes);
+int cb_host_unregister(void *p);
 int cb_stream_create(cb_stream *out);                     /* render.py:92,261 */
 int cb_stream_destroy(cb_stream s);
 int cb_stream_sync(cb_stream s);
@@ -254,6 +261,13 @@ typedef enum {
 int cb_convert(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
                const cb_dims *dim, cb_dptr seeds, int nstreams, cb_stream s);
 int cb_convert_size(cb_pixfmt fmt, const cb_dims *dim, size_t *bytes);
+/* The same for output rows [row0, row1) only (RGBA formats): every stream still draws
+ * the random numbers of the rows it skips, so bands converted separately -- e.g. one per
+ * GPU of a still whose filter chain is sharded by rows -- assemble into exactly the
+ * frame cb_convert produces, and the seeds end in the same state. */
+int cb_convert_rows(cb_pixfmt fmt, cb_dptr dst, cb_dptr src, int gutter,
+                    const cb_dims *dim, cb_dptr seeds, int nstreams, int row0,
+                    int row1, cb_stream s);
 
 /* ---- multi-GPU exchange (one process per GPU, NCCL over NVLink) ----------
  * The reference ships whole frames between worker processes

@@ -326,3 +326,51 @@ def test_frame_seed_keeps_rank_streams_disjoint(native, built):
         seeds[rank] = s
     assert not np.array_equal(seeds[0][:, 0], seeds[1][:, 0])       # disjoint multipliers
     assert not np.array_equal(seeds[0][:, 1:], seeds[1][:, 1:])
+
+
+@pytest.mark.gpu
+def test_banded_output_into_a_shared_frame_equals_the_whole_frame(native, built):
+    """Every rank filters its band, converts its own output rows (cb_convert_rows) and
+    copies them into one page-locked shared-memory frame: the assembled frame is
+    byte-identical to the frame rendered on one GPU.  One process plays the ranks in
+    turn on the same histogram."""
+    N = native
+    from cuburn_b200 import samples, render, profile, multigpu
+    gnm = samples.g6f()
+    w, h = 256, 1000
+    gprof = profile.wrap(dict(width=w, height=h, spp=40, frame_width=0, start=1, end=2), gnm)
+    tc = profile.enumerate_times(gprof)[0][1][0]
+    rmgr = render.RenderManager(seed=4)
+    rdr = render.Renderer(gnm, gprof)
+    # float reductions commute only up to rounding: pin the histogram so that every frame
+    # below is filtered from the same bits (the hook stands where the NCCL reduce would)
+    dim = rmgr.fb.set_dim(w, h)
+    rmgr._copy(rdr, gnm)
+    rmgr._interp(rdr, gnm, dim, tc, 0.0)
+    rmgr._iter(rdr, gnm, gprof, dim, tc)
+    rmgr.stream_a.synchronize()
+    hist = N.from_device(rmgr.fb.d_front, (dim.ah, dim.astride, 4), np.float32)
+    rmgr.hist_hook = lambda fb, dim_, stream: N.memcpy_htod(fb.d_front, hist, stream)
+    rmgr.fb.reseed(77)
+    evt, whole = rmgr.queue_frame(rdr, gnm, gprof, tc)
+    evt.synchronize()
+    whole = np.array(whole)
+    assert whole[..., :3].max() > 0
+    world = 4
+    shared = multigpu.SharedFrame(whole.shape, whole.dtype, 0, 1)
+    shared.array[:] = 0
+    covered = np.zeros(h, bool)
+    for rank in range(world):
+        rmgr.fb.reseed(77)                                  # same samples, same dither
+        rmgr.band_filter = multigpu.BandFilter(rank, world, comm=False, shared=shared)
+        assert rmgr.band_filter.comm is False
+        evt, out = rmgr.queue_frame(rdr, gnm, gprof, tc)
+        evt.synchronize()
+        assert out is shared.array
+        r0, r1 = rmgr.band_filter.output_rows(rmgr.fb.calc_dim(w, h), 12)
+        covered[r0:r1] = True
+        assert np.array_equal(shared.array[r0:r1], whole[r0:r1]), rank
+    rmgr.band_filter = None
+    assert covered.all()
+    assert np.array_equal(shared.array, whole)
+    shared.close()

@@ -116,3 +116,44 @@ def test_output_module_shapes(native, built):
         assert out.shape(dim) == shape and out.dtype == dt
     with pytest.raises(ValueError):
         output.get_output_for_profile(profile.wrap(dict(output=dict(type='gif')), {'type': 'animation'}))
+
+
+@pytest.mark.parametrize('fmt', ['rgba_u8', 'rgba_u16'])
+def test_convert_by_row_bands_equals_whole_frame(native, built, fmt):
+    """cb_convert_rows: a frame converted in three bands is byte-identical to the frame
+    converted at once, and the RNG streams end in the same state after every band."""
+    N = native
+    from cuburn_b200 import mwc
+    w, h = 96, 40
+    dim = N.calc_dim(w, h)
+    rs = np.random.RandomState(8)
+    src = rs.rand(dim.ah, dim.astride, 4).astype(np.float32)
+    src[rs.rand(dim.ah, dim.astride) < 0.2] = 0
+    code = {'rgba_u8': N.FMT_RGBA_U8, 'rgba_u16': N.FMT_RGBA_U16}[fmt]
+    px = 4 if fmt == 'rgba_u8' else 8
+    seeds = mwc.make_seeds(1024, host_seed=3)
+    d_src = N.to_device(src)
+
+    def run(bands):
+        d_seeds, d_dst = N.to_device(seeds), N.DeviceBuffer(w * h * px)
+        N.fill32(d_dst, w * h * px // 4, 0)
+        states = []
+        for r0, r1 in bands:
+            N.check(N.lib().cb_convert_rows(code, d_dst.ptr, d_src.ptr, 12, N.byref(dim),
+                                            d_seeds.ptr, 1024, r0, r1, None))
+            N.check(N.lib().cb_device_sync())
+            states.append(N.from_device(d_seeds, (1024, 3), np.uint32))
+        return N.from_device(d_dst, (h, w * px), np.uint8), states
+    whole, s_whole = run([(0, h)])
+    parts = []
+    for band in ((0, 13), (13, 14), (14, h)):
+        got, st = run([band])
+        assert np.array_equal(st[0], s_whole[0])
+        assert np.array_equal(got[band[0]:band[1]], whole[band[0]:band[1]])
+        assert not got[:band[0]].any() and not got[band[1]:].any()
+        parts.append(got[band[0]:band[1]])
+    assert np.array_equal(np.concatenate(parts), whole)
+    # planar formats convert whole frames only
+    with pytest.raises(N.NativeError):
+        N.check(N.lib().cb_convert_rows(N.FMT_YUV444P, 0, d_src.ptr, 12, N.byref(dim), 0, 1024,
+                                        0, 8, None))
