@@ -576,6 +576,7 @@ k_bilateral_fast(float4 *dst, const float4 *src, const float2 *side, int pattern
 struct bilat_tab {
     float lspa[16];             // log2 of the spatial kernel at |r|
     int loff[BW_MAXREC];        // linear offset of window record k (s = k - 16)
+    int loff2[BW_MAXREC];       // the same in the pitch of a staged `side` tile (tile kernel)
     short2 off[BW_MAXREC];      // (dx, dy) of window record k
     int xlo, xhi, ylo, yhi;     // extent of the window offsets
 };
@@ -676,12 +677,25 @@ struct bilat_duos<S, K, BW_P / 2> {
 // at the edge of the grid clamp each coordinate like the reference's texture fetch.
 // Clamping commutes with sharing: tap r of pixel j and record S j + r + 16 are the
 // same position before the clamp, hence after it.
-template <bool INTERIOR>
+// MODE 0: clamped (blocks at the edge of the grid), 1: interior of the global planes,
+// 2: a tile staged in shared memory (src and side tiles have their own pitches, the
+// result goes to the global plane).
+template <int MODE>
 struct bilat_addr {
-    int c0, x, y0, W, H;
+    int c0, x, y0, W, H;        // source position (MODE 2: inside the tile)
+    int c1;                     // MODE 2: base index into the side tile
+    int xd, yd, Wd;             // MODE 2: where the thread's first pixel lives in dst
     __device__ __forceinline__ int operator()(const bilat_tab &tab, int k) const {
-        if (INTERIOR) return c0 + tab.loff[k];
+        if (MODE != 0) return c0 + tab.loff[k];
         return clamp_idx(x + tab.off[k].x, y0 + tab.off[k].y, W, H);
+    }
+    __device__ __forceinline__ int side_idx(const bilat_tab &tab, int k) const {
+        if (MODE == 2) return c1 + tab.loff2[k];
+        return (*this)(tab, k);
+    }
+    __device__ __forceinline__ int store_idx(short2 o) const {
+        if (MODE == 2) return (yd + o.y) * Wd + xd + o.x;
+        return (y0 + o.y) * W + x + o.x;
     }
 };
 
@@ -692,7 +706,7 @@ struct bilat_addr {
 #endif
 struct bilat_raw { float4 pix; float2 side; };
 
-template <int K, int KEND, bool INTERIOR>
+template <int K, int KEND, int INTERIOR>
 __device__ __forceinline__ bilat_raw bilat_load(const float4 *src, const float2 *side,
                                                 const bilat_addr<INTERIOR> &at,
                                                 const bilat_tab &tab) {
@@ -700,16 +714,15 @@ __device__ __forceinline__ bilat_raw bilat_load(const float4 *src, const float2 
     r.pix = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     r.side = make_float2(0.0f, 0.0f);
     if (K < KEND) {                 // a tap: the whole record
-        const int i = at(tab, K);
-        r.pix = src[i];
-        r.side = side[i];
+        r.pix = src[at(tab, K)];
+        r.side = side[at.side_idx(tab, K)];
     } else if (K == KEND) {         // past the last tap: only its density is read
         r.pix.w = src[at(tab, K)].w;
     }
     return r;
 }
 
-template <int S, int K, int KEND, bool INTERIOR>
+template <int S, int K, int KEND, int INTERIOR>
 struct bilat_window {
     // ring[i] holds record K + i, i = 0 .. BW_AHEAD
     static __device__ __forceinline__ void run(
@@ -739,7 +752,7 @@ struct bilat_window {
         bilat_window<S, K + 1, KEND, INTERIOR>::run(src, side, at, cur.w, ring, duo, tab, kc);
     }
 };
-template <int S, int KEND, bool INTERIOR>
+template <int S, int KEND, int INTERIOR>
 struct bilat_window<S, KEND, KEND, INTERIOR> {
     static __device__ __forceinline__ void run(const float4 *, const float2 *,
                                                const bilat_addr<INTERIOR> &, float, bilat_raw *,
@@ -796,23 +809,22 @@ __device__ __noinline__ void bilat_pixel_clamped(
 // The window of one thread.  Pixels whose sheared position leaves the grid in x belong
 // to the other side of the row (the block shapes tile the row cyclically): the few
 // threads that own such pixels redo them with the per-pixel path.
-template <int S, bool INTERIOR>
+template <int S, int INTERIOR>
 __device__ __forceinline__ void bilat_window_thread(
-        float4 *dst, const float4 *src, const float2 *side, int x, int y0,
-        const bilat_tab &tab, const bilat_consts &kc, int W, int H) {
-    bilat_addr<INTERIOR> at;
-    at.c0 = y0 * W + x; at.x = x; at.y0 = y0; at.W = W; at.H = H;
+        float4 *dst, const float4 *src, const float2 *side, const bilat_addr<INTERIOR> &at,
+        const bilat_tab &tab, const bilat_consts &kc) {
+    const int x = at.x, y0 = at.y0, W = at.W, H = at.H;
     bilat_duo duo[BW_P / 2];
 #pragma unroll
     for (int d = 0; d < BW_P / 2; d++) {
         float nc[2][3];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int ci = at(tab, S * (2 * d + h) + 16);
-            const float4 cen = src[ci];
+            const int k = S * (2 * d + h) + 16;
+            const float4 cen = src[at(tab, k)];
             const float cdrcp = 1.0f / (cen.w + 1.0e-6f);
             nc[h][0] = -(cen.x * cdrcp); nc[h][1] = -(cen.y * cdrcp); nc[h][2] = -(cen.z * cdrcp);
-            (h ? duo[d].cpow1 : duo[d].cpow0) = side[ci].y;
+            (h ? duo[d].cpow1 : duo[d].cpow0) = side[at.side_idx(tab, k)].y;
             (h ? duo[d].live1 : duo[d].live0) = cen.w > 0.0f;
         }
         duo[d].ncx = pk2(nc[0][0], nc[1][0]);
@@ -844,12 +856,12 @@ __device__ __forceinline__ void bilat_window_thread(
         for (int h = 0; h < 2; h++) {
             const short2 o = tab.off[S * (2 * d + h) + 16];
             const int xj = x + o.x, yj = y0 + o.y;
-            if (!INTERIOR && (yj >= H || xj < 0 || xj >= W)) continue;
+            if (INTERIOR == 0 && (yj >= H || xj < 0 || xj >= W)) continue;
             const float rcp = 1.0f / (ws[h] + 1e-10f);
-            dst[yj * W + xj] = make_float4(ax[h] * rcp, ay[h] * rcp, az[h] * rcp, aw[h] * rcp);
+            dst[at.store_idx(o)] = make_float4(ax[h] * rcp, ay[h] * rcp, az[h] * rcp, aw[h] * rcp);
         }
     }
-    if (!INTERIOR) {
+    if (INTERIOR == 0) {
 #pragma unroll 1
         for (int j = 0; j < BW_P; j++) {
             const short2 o = tab.off[S * j + 16];
@@ -875,10 +887,99 @@ k_bilateral_window(float4 *dst, const float4 *src, const float2 *side,
                           : yb + (threadIdx.y >> 2) * 16 + (threadIdx.y & 3);
     const bool interior = x0 + tab.xlo >= 0 && x0 + 31 + tab.xhi < W &&
                           yb + tab.ylo >= 0 && yb + 31 + tab.yhi < H;
-    if (interior)
-        bilat_window_thread<S, true>(dst, src, side, x, y0, tab, kc, W, H);
-    else if (y0 < H)
-        bilat_window_thread<S, false>(dst, src, side, x, y0, tab, kc, W, H);
+    if (interior) {
+        bilat_addr<1> at;
+        at.c0 = y0 * W + x; at.x = x; at.y0 = y0; at.W = W; at.H = H;
+        bilat_window_thread<S, 1>(dst, src, side, at, tab, kc);
+    } else if (y0 < H) {
+        bilat_addr<0> at;
+        at.c0 = y0 * W + x; at.x = x; at.y0 = y0; at.W = W; at.H = H;
+        bilat_window_thread<S, 0>(dst, src, side, at, tab, kc);
+    }
+}
+
+// ---- x-major directions: the same window over a tile staged in shared memory ----------
+// For the directions whose taps advance one column per step -- (1,0): S = 1; (1,+-.5):
+// S = 4 -- the records a thread walks lie along a row, so lanes along x would read the
+// same addresses and lanes along y would read global memory with a stride of one row.
+// Here a block stages the rows it needs (64 columns of float4 and float2 records, 32 to
+// 54 rows) in shared memory with one bulk asynchronous copy per row and plane
+// (cp.async.bulk, the TMA engine; completion on an mbarrier), and lanes run along y:
+// row pitches of 65 float4 / 66 float2 keep the column-wise reads free of bank conflicts.
+// A thread owns BW_P pixels S steps apart along the direction as in the y-major kernel;
+// for S = 4 a block therefore covers a sheared set of pixels (column c of the block is
+// shifted by +-2 * ((c % 16) / 4) rows) that tiles the plane vertically with period
+// 32 * gridDim.y.  Blocks whose tile leaves the grid run the per-pixel clamped path.
+#define BT_COLS 64
+#define BT_PITCH4 65            // float4 elements per tile row (1040 B: 16 B bank shift per row)
+#define BT_PITCH2 66            // float2 elements per tile row (528 B, a multiple of 16)
+#define BT_MAXROWS 54
+
+__device__ __forceinline__ unsigned int smem_u32(const void *p) {
+    return (unsigned int)__cvta_generic_to_shared(p);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, BW_MIN_CTAS)
+k_bilateral_tile(float4 *dst, const float4 *src, const float2 *side,
+                 const __grid_constant__ bilat_tab tab, bilat_consts kc, cb_dims dim) {
+    extern __shared__ __align__(128) unsigned char bt_smem[];
+    const int W = dim.astride, H = dim.aheight;
+    const int x0 = blockIdx.x * 32, yb = blockIdx.y * 32;
+    const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+    // first column of this thread's pixels inside the block
+    const int cs = S == 1 ? warp * BW_P : (warp >> 2) * 16 + (warp & 3);
+    const int nrows = 32 + tab.yhi - tab.ylo;
+    const bool interior = x0 - 16 >= 0 && x0 + 48 <= W && yb + tab.ylo >= 0 &&
+                          yb + 31 + tab.yhi < H;
+    if (interior) {
+        float4 *t4 = reinterpret_cast<float4 *>(bt_smem);
+        float2 *t2 = reinterpret_cast<float2 *>(bt_smem + nrows * BT_PITCH4 * 16);
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(
+            bt_smem + nrows * (BT_PITCH4 * 16 + BT_PITCH2 * 8));
+        const unsigned int bar_a = smem_u32(bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         :: "r"(bar_a), "r"(nrows * (BT_COLS * 16 + BT_COLS * 8)) : "memory");
+        if (tid < nrows) {
+            const size_t g = (size_t)(yb + tab.ylo + tid) * W + (x0 - 16);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(t4 + tid * BT_PITCH4)), "l"(src + g),
+                            "r"(BT_COLS * 16), "r"(bar_a) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(t2 + tid * BT_PITCH2)), "l"(side + g),
+                            "r"(BT_COLS * 8), "r"(bar_a) : "memory");
+        }
+        unsigned int done;
+        do {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                         " selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a) : "memory");
+        } while (!done);
+        bilat_addr<2> at;
+        const int row = lane - tab.ylo, col = cs + 16;
+        at.c0 = row * BT_PITCH4 + col;
+        at.c1 = row * BT_PITCH2 + col;
+        at.x = col; at.y0 = row; at.W = BT_PITCH4; at.H = nrows;
+        at.xd = x0 + cs; at.yd = yb + lane; at.Wd = W;
+        bilat_window_thread<S, 2>(dst, t4, t2, at, tab, kc);
+    } else {
+        const int wrap = 32 * gridDim.y;
+#pragma unroll 1
+        for (int j = 0; j < BW_P; j++) {
+            const short2 o = tab.off[S * j + 16];
+            int yj = yb + lane + o.y;
+            yj = yj < 0 ? yj + wrap : (yj >= wrap ? yj - wrap : yj);
+            if (yj < H)
+                bilat_pixel_clamped(dst, src, side, x0 + cs + o.x, yj, tab, kc, W, H);
+        }
+    }
 }
 
 // Host copy of the first eight entries of c_dirs, for the window tables.
@@ -895,7 +996,15 @@ static int bilat_window_step(int pattern) {
     return 0;
 }
 
-static bilat_tab make_bilat_tab(int pattern, int step, float sstd, int astride) {
+// Direction step of the x-major directions handled by k_bilateral_tile, 0 for the others.
+static int bilat_tile_step(int pattern) {
+    if (pattern == 0) return 1;
+    if (pattern == 4 || pattern == 6) return 4;
+    return 0;
+}
+
+// pitch / pitch2: elements per row of the plane (or staged tile) the linear offsets index
+static bilat_tab make_bilat_tab(int pattern, int step, float sstd, int pitch, int pitch2 = 0) {
     bilat_tab t;
     memset(&t, 0, sizeof(t));
     const float log2e = 1.44269502162933f;
@@ -908,7 +1017,8 @@ static bilat_tab make_bilat_tab(int pattern, int step, float sstd, int astride) 
         const int dx = (int)nearbyintf(h_dirs[pattern][0] * s);
         const int dy = (int)nearbyintf(h_dirs[pattern][1] * s);
         t.off[k] = make_short2((short)dx, (short)dy);
-        t.loff[k] = dy * astride + dx;
+        t.loff[k] = dy * pitch + dx;
+        t.loff2[k] = dy * pitch2 + dx;
         t.xlo = dx < t.xlo ? dx : t.xlo;
         t.xhi = dx > t.xhi ? dx : t.xhi;
         t.ylo = dy < t.ylo ? dy : t.ylo;
@@ -1103,13 +1213,32 @@ static int bilateral_main(float4 *dst, const float4 *src, const float2 *side, in
                           int radius, float sstd, float cstd, float dstd, float gspeed,
                           const cb_dims *dim, cb_stream s) {
     const int step = radius == 15 ? bilat_window_step(pattern) : 0;
-    if (step) {
+    const int tstep = radius == 15 ? bilat_tile_step(pattern) : 0;
+    bilat_consts kc;
+    kc.cscale2 = 1.44269502162933f / (-K_SQRT2 * 3.0f * cstd);
+    kc.dscale = -0.5f / dstd;
+    kc.gspeed = gspeed;
+    const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
+    if (tstep && dim->astride >= 96) {
+        const bilat_tab tab = make_bilat_tab(pattern, tstep, sstd, BT_PITCH4, BT_PITCH2);
+        const int nrows = 32 + tab.yhi - tab.ylo;
+        const int smem = nrows * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16;
+        static bool configured = false;
+        if (!configured) {
+            CB_CUDA(cudaFuncSetAttribute(k_bilateral_tile<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         BT_MAXROWS * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16));
+            CB_CUDA(cudaFuncSetAttribute(k_bilateral_tile<4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         BT_MAXROWS * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16));
+            configured = true;
+        }
+        if (tstep == 1)
+            k_bilateral_tile<1><<<grid, dim3(32, 8), smem, cb_cs(s)>>>(dst, src, side, tab, kc, *dim);
+        else
+            k_bilateral_tile<4><<<grid, dim3(32, 8), smem, cb_cs(s)>>>(dst, src, side, tab, kc, *dim);
+    } else if (step) {
         const bilat_tab tab = make_bilat_tab(pattern, step, sstd, dim->astride);
-        bilat_consts kc;
-        kc.cscale2 = 1.44269502162933f / (-K_SQRT2 * 3.0f * cstd);
-        kc.dscale = -0.5f / dstd;
-        kc.gspeed = gspeed;
-        const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
         if (step == 1)
             k_bilateral_window<1><<<grid, dim3(32, 8), 0, cb_cs(s)>>>(dst, src, side, tab, kc, *dim);
         else

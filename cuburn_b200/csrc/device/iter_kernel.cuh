@@ -59,7 +59,7 @@ struct iter_args {
     unsigned long long nsamples;
     unsigned long long total_samples;
     unsigned long long *cells;                 // ACC_PACKED: u64 [aheight][astride]
-    const unsigned long long *palette_packed;  // ACC_PACKED / HOT_BINS: u64 [pal_rows][256]
+    const unsigned long long *palette_packed;  // u64 [pal_rows][256] (ACC_PACKED, PAL_COMPACT)
     const int *hot_tags;                       // HOT_BINS: int [HOT_SLOTS + 1]: bin or -1, then the hash multiplier
     int first_round;        // phase of the exchange permutation to start from
 };
@@ -72,6 +72,20 @@ struct iter_args {
 #endif
 #ifndef HOT_BINS
 #define HOT_BINS 0
+#endif
+// PAL_COMPACT: the unit's palette row is staged as 8-bit levels (Y << 16 | U << 8 | V, one
+// 32-bit word per entry) instead of float4: the per-sample colour fetch becomes an LDS.32
+// (1 KB table, ~3 shared-memory wavefronts per warp instead of ~9 for the 16-byte
+// gather) followed by three byte-to-float conversions.  The float4 table holds exactly
+// level * (1 / 255) (cb_interp_palette), so the contribution is bit-identical.  Pays
+// where the kernel is bound by L1TEX wavefronts (motion blur: parameters in shared
+// memory), costs issue slots where it is not (profiles/r02_iter_variants.md).
+#ifndef PAL_COMPACT
+#define PAL_COMPACT (HOT_BINS || !PARAMS_CONST)
+#endif
+#if ACC_PACKED
+#undef PAL_COMPACT
+#define PAL_COMPACT 0
 #endif
 // Slots of the per-CTA hot-bin table: a direct-mapped multiplicative hash of the bin
 // index; cb_hot_scan picks, per frame, the multiplier (out of eight) that places most
@@ -292,31 +306,46 @@ typedef float4 pal_entry;
 
 struct iter_smem {
     xchg_buf xb[2];
+#if PAL_COMPACT
+    unsigned int palc[256];             // the unit's palette row as 8-bit levels
+#else
     pal_entry pal[256];
+#endif
 #if HOT_BINS
-    unsigned long long palp[256];       // the unit's palette row as packed 8-bit levels
     hot_table hot;
     unsigned int hot_mul;
 #endif
 };
+
+__device__ __forceinline__ unsigned int compact_levels(unsigned long long packed) {
+    return ((unsigned int)(packed >> 36) & 0xffu) << 16 |
+           ((unsigned int)(packed >> 18) & 0xffu) << 8 | ((unsigned int)packed & 0xffu);
+}
 
 __device__ __forceinline__ void record_sample(const iter_args &a, iter_smem &sm, int bin,
                                               unsigned int cidx, unsigned int word, int lane) {
 #if ACC_PACKED
     accumulate_packed(a.cells + bin, a.hist + bin, sm.pal[cidx], (word & 31u) == (unsigned int)lane);
 #else
+#if PAL_COMPACT
+    const unsigned int lv = sm.palc[cidx];
 #if HOT_BINS
     const unsigned int hs = hot_slot(bin, sm.hot_mul);
     if (sm.hot.tag[hs] == bin) {
-        const unsigned long long p = sm.palp[cidx];
         atomicAdd(&sm.hot.cell[hs][0], 1u);
-        atomicAdd(&sm.hot.cell[hs][1], (unsigned int)(p >> 36) & 0xffu);
-        atomicAdd(&sm.hot.cell[hs][2], (unsigned int)(p >> 18) & 0xffu);
-        atomicAdd(&sm.hot.cell[hs][3], (unsigned int)p & 0xffu);
+        atomicAdd(&sm.hot.cell[hs][1], lv >> 16);
+        atomicAdd(&sm.hot.cell[hs][2], (lv >> 8) & 0xffu);
+        atomicAdd(&sm.hot.cell[hs][3], lv & 0xffu);
         return;
     }
 #endif
+    const float k = 1.0f / 255.0f;
+    red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins),
+                  make_float4(__uint2float_rn(lv >> 16) * k, __uint2float_rn((lv >> 8) & 0xffu) * k,
+                              __uint2float_rn(lv & 0xffu) * k, 1.0f));
+#else
     red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), sm.pal[cidx]);
+#endif
 #endif
 }
 
@@ -374,11 +403,10 @@ cb_iter(const __grid_constant__ iter_args a) {
         if (row != cur_row) {
 #if ACC_PACKED
             sm.pal[tid] = a.palette_packed[row * 256 + tid];
+#elif PAL_COMPACT
+            sm.palc[tid] = compact_levels(a.palette_packed[row * 256 + tid]);
 #else
             sm.pal[tid] = a.palette[row * 256 + tid];
-#endif
-#if HOT_BINS
-            sm.palp[tid] = a.palette_packed[row * 256 + tid];
 #endif
             cur_row = row;
         }

@@ -287,6 +287,8 @@ class RenderManager(object):
         self.d_hot = N.DeviceBuffer(HOT_BYTES)
         N.fill32(self.d_hot, HOT_BYTES // 4, 0)
         self._hot_probe = None          # (event, pinned count, renderer) of the last scan
+        self._hot_counts = self.fb.pool.allocate((8,), 'i4')       # pinned ring of results
+        self._hot_seq = 0
         # share of the frame's samples this manager renders (multi-GPU stills)
         self.sample_share = (rank, world)
         self.hist_hook = None
@@ -453,6 +455,7 @@ class RenderManager(object):
             mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
         fuse, first_round = info.fuse, 0
         n_frame = n
+        probe = None
         if pilot:
             # whole waves of the persistent grid, about 1/hot_pilot of the frame
             npilot = grid * max(1, round(nunits / float(self.hot_pilot * grid))) * UNIT_SAMPLES
@@ -462,14 +465,14 @@ class RenderManager(object):
                 self.d_hot.ptr + HOT_TAGS_OFF, self.d_hot.ptr + HOT_COUNT_OFF, self.d_hot.ptr,
                 int(d_acc), swz, np.float32(max(32.0, self.hot_share * npilot)),
                 np.float32(max(32.0, self.hot_trigger * npilot)), N.byref(dim), s.handle))
-            count = self.fb.pool.allocate((1,), 'i4')
-            N.memcpy_dtoh(count, N.DeviceSlice(self.d_hot, HOT_COUNT_OFF, 4), s)
-            evt = N.Event().record(s)
-            self._hot_probe = (evt, count, rdr)
-            self._pinned.append((count,))
+            self._hot_seq = (self._hot_seq + 1) % 8
+            probe = self._hot_counts[self._hot_seq:self._hot_seq + 1]
             if hot is None:
-                evt.synchronize()
-                hot = rdr.hot = bool(count[0] > 0)
+                # first frame of this genome: the variant depends on the answer
+                N.memcpy_dtoh(probe, N.DeviceSlice(self.d_hot, HOT_COUNT_OFF, 4), s)
+                s.synchronize()
+                hot = rdr.hot = bool(probe[0] > 0)
+                probe = None
             # the pilot is whole waves: every CTA has run the same number of rounds
             first_round = fuse + (npilot // UNIT_SAMPLES // grid) * (UNIT_SAMPLES // ITER_THREADS)
             first, n, fuse = first + npilot, n - npilot, 0
@@ -480,6 +483,11 @@ class RenderManager(object):
         if n > 0:
             self._launch_iter(mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
                               bool(hot), s, first_round)
+        if probe is not None:
+            # read the scan's verdict back behind the main launch (nothing between the pilot
+            # and the main launch may wait on the host); the next frame picks it up
+            N.memcpy_dtoh(probe, N.DeviceSlice(self.d_hot, HOT_COUNT_OFF, 4), s)
+            self._hot_probe = (N.Event().record(s), probe, rdr)
         if packed:
             N.check(N.lib().cb_flush_packed(self.fb.d_front.ptr, self.fb.d_left.ptr,
                                             N.byref(dim), s.handle))

@@ -144,7 +144,7 @@ def test_bilateral_pass(native, built, pattern, kind):
     assert abs(got[..., 3].sum() / f[..., 3].sum() - 1) < 0.35
 
 
-@pytest.mark.parametrize('pattern', [0, 2, 5, 7])
+@pytest.mark.parametrize('pattern', [0, 2, 4, 5, 6, 7])
 @pytest.mark.parametrize('kind', ['mixed', 'points', 'dense'])
 def test_bilateral_direction_fused(native, built, pattern, kind):
     """The restructured direction pass (hoisted per-pixel terms, one exp2 per tap)
@@ -180,6 +180,43 @@ def test_bilateral_direction_fused(native, built, pattern, kind):
     N.check(L.cb_device_sync())
     ref = N.from_device(d_ref, f.shape, np.float32)
     assert (np.abs(got - ref) > 1e-3 * scale + 1e-3 * np.abs(ref)).mean() < 1e-3
+
+
+@pytest.mark.parametrize('pattern,twin', [(0, 1), (4, 7), (6, 5)])
+def test_tile_kernel_equals_the_window_kernel_on_the_transposed_field(native, built, pattern, twin):
+    """The x-major directions run over a shared-memory tile staged by bulk asynchronous
+    copies (k_bilateral_tile); transposing the field turns them into the y-major
+    directions of k_bilateral_window, which walk the same records in the same order:
+    (1,0) <-> (0,1), (1,.5) <-> (.5,1), (1,-.5) <-> (-.5,1).  Square 224 x 224 grid with
+    structure at all four edges, so interior tiles, clamped edge blocks and the
+    vertically wrapping sheared blocks are all exercised."""
+    N = native
+    from cuburn_b200.filters import gauss_coefs
+    n = 224
+    dim = N.Dims(n - 24, n - 24, n, n, n)
+    rs = np.random.RandomState(pattern)
+    yy, xx = np.mgrid[0:n, 0:n]
+    den = 30 * np.exp(-((xx - 80) ** 2 + (yy - 130) ** 2) / 900.0) + rs.gamma(0.5, 4.0, (n, n))
+    den[rs.rand(n, n) < 0.25] = 0
+    den[:, :3] += 20; den[:2, :] += 15; den[-3:, :] += 9; den[:, -2:] += 11
+    f = np.zeros((n, n, 4), np.float32)
+    f[..., 3] = den
+    for ch in range(3):
+        f[..., ch] = den * rs.uniform(0.2, 0.9, (n, n))
+    args = (15, gauss_coefs(1), np.float32(6 * 4.0), np.float32(0.05), np.float32(1.5),
+            np.float32(0.8), np.float32(4.0))
+
+    def run(field, pat):
+        src, scratch, out = upload_field(N, field), N.DeviceBuffer(field.nbytes), N.DeviceBuffer(field.nbytes)
+        N.check(N.lib().cb_bilateral_direction(out.ptr, src.ptr, scratch.ptr, pat, *args,
+                                               N.byref(dim), None))
+        N.check(N.lib().cb_device_sync())
+        return N.from_device(out, field.shape, np.float32)
+    got = run(f, pattern)
+    want = run(np.ascontiguousarray(f.transpose(1, 0, 2)), twin).transpose(1, 0, 2)
+    assert np.isfinite(got).all() and got[..., 3].max() > 1
+    scale = float(np.abs(want).max())
+    assert np.abs(got - want).max() <= 2e-6 * scale, float(np.abs(got - want).max() / scale)
 
 
 def test_pointwise_tonemap_kernels(native, built):

@@ -618,6 +618,7 @@ def test_packed_accumulation_equals_float4(native, built):
     for mode in ('float4', 'packed'):
         rmgr = render.RenderManager(seed=17)
         rmgr.accumulate = mode
+        rmgr.hot_bins = False               # one launch each: the same sample set
         rdr = render.Renderer(gnm, gprof)
         dim = rmgr.fb.set_dim(w, h)
         rmgr._copy(rdr, gnm)

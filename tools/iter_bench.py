@@ -23,7 +23,7 @@ cases += [('G4M', 1920, 1080, 2000), ('G3F', 1920, 1080, 2000), ('G2M', 1920, 10
 if os.environ.get('CASES'):
     cases = [c for c in cases if c[0] in os.environ['CASES'].split(',')]
 variants = sys.argv[1:] or ['']
-rmgr = render.RenderManager(seed=1); rmgr.swizzle = {'1': True, '0': False}.get(os.environ.get('SWZ', 'auto'), 'auto')
+rmgr = render.RenderManager(seed=1); rmgr.hot_bins = False; rmgr.swizzle = {'1': True, '0': False}.get(os.environ.get('SWZ', 'auto'), 'auto')
 for gname, w, h, spp in cases:
     gnm = samples.GENOMES[gname]()
     gprof = profile.wrap(dict(width=w, height=h, spp=spp, frame_width=0, start=1, end=2), gnm)
