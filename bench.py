@@ -327,6 +327,7 @@ def run_still(b, name, steps, warmup, sampler=None):
                               frame_width=0, start=1, end=2), gnm)
     tc = profile.enumerate_times(gprof)[0][1][0]
     rmgr = render.RenderManager(seed=1, rank=b.rank, world=b.world)
+    rmgr.hot_bins = {'auto': 'auto', 'off': False, 'on': True}[args.hot_bins]
     rdr = render.Renderer(gnm, gprof)
     dim = rmgr.fb.set_dim(gprof.width, gprof.height)
     reducer = shared = None
@@ -492,6 +493,8 @@ def main():
     ap.add_argument('--collectives', default='torch', choices=['torch', 'native'],
                     help="multi-GPU exchange through torch.distributed or through the "
                          "library's own NCCL communicator (cb_hist_reduce / cb_band_gather)")
+    ap.add_argument('--hot-bins', default='auto', choices=['auto', 'off', 'on'],
+                    help='hot-bin privatisation: probe per genome (default), never, always')
     ap.add_argument('--workload', default='still1080',
                     choices=['still1080', 'still4k', 'still8k'],
                     help='headline workload: still1080 = BASELINE configs[1] (default)')

@@ -107,6 +107,7 @@ _SIGNATURES = {
     'cb_module_get_cubin': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t)]),
     'cb_module_kernel_info': (c_int, [c_void_p, c_char_p, c_int, POINTER(c_int),
                                       POINTER(c_int), POINTER(c_int)]),
+    'cb_module_kernel_local_bytes': (c_int, [c_void_p, c_char_p, POINTER(c_int)]),
     'cb_module_launch': (c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, POINTER(c_void_p), c_void_p]),
     'cb_module_set_global': (c_int, [c_void_p, c_char_p, c_uint64, c_size_t, c_void_p]),
@@ -428,6 +429,12 @@ class Module(object):
         check(lib().cb_module_kernel_info(self.handle, kernel.encode(), block_threads,
                                           byref(regs), byref(smem), byref(ctas)))
         return dict(num_regs=regs.value, static_smem=smem.value, ctas_per_sm=ctas.value)
+
+    def local_bytes(self, kernel):
+        """Local memory per thread (spills) of a kernel."""
+        n = c_int()
+        check(lib().cb_module_kernel_local_bytes(self.handle, kernel.encode(), byref(n)))
+        return n.value
 
     def set_global(self, symbol, src, nbytes, stream=None):
         check(lib().cb_module_set_global(self.handle, symbol.encode(), int(src), int(nbytes),

@@ -62,10 +62,17 @@ class GenomePacker(object):
         wrows = [self._row(('xforms', xid, 'weight')) for xid in self.xform_ids]
         assert wrows == list(range(len(wrows)))
 
+        # Every block of slots that is read together (one xform, the choice densities, the
+        # camera) starts on a 16-byte boundary: with the parameters in shared memory
+        # (motion blur) the kernel fetches them as aligned float4s, and a block that
+        # straddles a boundary costs an extra shared-memory wavefront per warp and round.
         for xid in self.xform_ids:
+            self._align()
             self._add_xform(('xforms', xid), gnm['xforms'][xid])
         if self.has_final:
+            self._align()
             self._add_xform(('final_xform',), gnm['final_xform'])
+        self._align()
 
         if len(self.xform_ids) > 1 and not self.xaos:
             first = None
@@ -81,6 +88,7 @@ class GenomePacker(object):
                 first = self._slot_block(('xforms', pid, 'chaos_den'), self.xform_ids[:-1])
                 self._op(OP_XAOS, first, [wrows[0], crows[0]], aux0=len(self.xform_ids))
 
+        self._align()
         cam_rows = [self._row(('camera', 'rotation')),
                     self._row(('camera', 'center', 'x')),
                     self._row(('camera', 'center', 'y')),
@@ -153,6 +161,15 @@ class GenomePacker(object):
         self._slot_index[name] = len(self.slot_names)
         self.slot_names.append(name)
         return self._slot_index[name]
+
+    def _align(self, n=4):
+        """Pad with unnamed slots up to a multiple of ``n``."""
+        while len(self.slot_names) % n:
+            self.slot_names.append('_pad.%d' % len(self.slot_names))
+
+    def named_slots(self):
+        """[(slot index, dotted name)] of the slots that carry a parameter."""
+        return [(i, n) for i, n in enumerate(self.slot_names) if not n.startswith('_pad.')]
 
     def _slot_block(self, path, names):
         first = None

@@ -11,6 +11,7 @@
 // with clamp-to-edge indices.  This file is compiled with
 // --use_fast_math like the reference's modules (code/util.py:96).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cb_common.h"
@@ -694,7 +695,9 @@ struct bilat_addr {
         return (*this)(tab, k);
     }
     __device__ __forceinline__ int store_idx(short2 o) const {
-        if (MODE == 2) return (yd + o.y) * Wd + xd + o.x;
+        // MODE 2: results go to an output tile indexed (lane, column in the block); the
+        // row shift of the sheared block shape is applied when the tile is written out
+        if (MODE == 2) return yd * Wd + xd + o.x;
         return (y0 + o.y) * W + x + o.x;
     }
 };
@@ -906,6 +909,8 @@ k_bilateral_window(float4 *dst, const float4 *src, const float2 *side,
 // 54 rows) in shared memory with one bulk asynchronous copy per row and plane
 // (cp.async.bulk, the TMA engine; completion on an mbarrier), and lanes run along y:
 // row pitches of 65 float4 / 66 float2 keep the column-wise reads free of bank conflicts.
+// Results are staged in a 32 x 32 output tile (pitch 33) and written out with lanes along
+// x, so the stores are coalesced as well.
 // A thread owns BW_P pixels S steps apart along the direction as in the y-major kernel;
 // for S = 4 a block therefore covers a sheared set of pixels (column c of the block is
 // shifted by +-2 * ((c % 16) / 4) rows) that tiles the plane vertically with period
@@ -914,6 +919,8 @@ k_bilateral_window(float4 *dst, const float4 *src, const float2 *side,
 #define BT_PITCH4 65            // float4 elements per tile row (1040 B: 16 B bank shift per row)
 #define BT_PITCH2 66            // float2 elements per tile row (528 B, a multiple of 16)
 #define BT_MAXROWS 54
+#define BT_OPITCH 33            // float4 elements per row of the output tile
+#define BT_OUT_BYTES (32 * BT_OPITCH * 16)
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) {
     return (unsigned int)__cvta_generic_to_shared(p);
@@ -937,6 +944,8 @@ k_bilateral_tile(float4 *dst, const float4 *src, const float2 *side,
         float2 *t2 = reinterpret_cast<float2 *>(bt_smem + nrows * BT_PITCH4 * 16);
         unsigned long long *bar = reinterpret_cast<unsigned long long *>(
             bt_smem + nrows * (BT_PITCH4 * 16 + BT_PITCH2 * 8));
+        float4 *tout = reinterpret_cast<float4 *>(
+            bt_smem + nrows * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16);
         const unsigned int bar_a = smem_u32(bar);
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
@@ -967,8 +976,15 @@ k_bilateral_tile(float4 *dst, const float4 *src, const float2 *side,
         at.c0 = row * BT_PITCH4 + col;
         at.c1 = row * BT_PITCH2 + col;
         at.x = col; at.y0 = row; at.W = BT_PITCH4; at.H = nrows;
-        at.xd = x0 + cs; at.yd = yb + lane; at.Wd = W;
-        bilat_window_thread<S, 2>(dst, t4, t2, at, tab, kc);
+        at.xd = cs; at.yd = lane; at.Wd = BT_OPITCH;
+        bilat_window_thread<S, 2>(tout, t4, t2, at, tab, kc);
+        __syncthreads();
+        // column c of the block belongs to pixel j of its thread: shifted by off(S j).y rows
+        const int j = S == 1 ? (lane & 3) : ((lane & 15) >> 2);
+        const int shift = tab.off[S * j + 16].y;
+#pragma unroll
+        for (int r = warp; r < 32; r += 8)
+            dst[(size_t)(yb + r + shift) * W + x0 + lane] = tout[r * BT_OPITCH + lane];
     } else {
         const int wrap = 32 * gridDim.y;
 #pragma unroll 1
@@ -1219,18 +1235,27 @@ static int bilateral_main(float4 *dst, const float4 *src, const float2 *side, in
     kc.dscale = -0.5f / dstd;
     kc.gspeed = gspeed;
     const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
-    if (tstep && dim->astride >= 96) {
+    // Measured (profiles/r02_filter_kernels.md): the staged tile wins once a plane no longer
+    // fits L2 (4K: 380 vs 436 us for (1,0)); at 1080p the one-pixel-per-thread kernel,
+    // whose loads overlap its arithmetic, is faster (127 vs 153 us).  CB_BILAT_TILE=0/1
+    // forces the choice (tests run both).
+    const char *force = getenv("CB_BILAT_TILE");
+    const bool tile = force ? force[0] == '1'
+                            : (size_t)nbins(dim) * sizeof(float4) > ((size_t)96 << 20);
+    if (tstep && tile && dim->astride >= 96) {
         const bilat_tab tab = make_bilat_tab(pattern, tstep, sstd, BT_PITCH4, BT_PITCH2);
         const int nrows = 32 + tab.yhi - tab.ylo;
-        const int smem = nrows * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16;
+        const int smem = nrows * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16 + BT_OUT_BYTES;
         static bool configured = false;
         if (!configured) {
             CB_CUDA(cudaFuncSetAttribute(k_bilateral_tile<1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         BT_MAXROWS * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16));
+                                         BT_MAXROWS * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16 +
+                                             BT_OUT_BYTES));
             CB_CUDA(cudaFuncSetAttribute(k_bilateral_tile<4>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         BT_MAXROWS * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16));
+                                         BT_MAXROWS * (BT_PITCH4 * 16 + BT_PITCH2 * 8) + 16 +
+                                             BT_OUT_BYTES));
             configured = true;
         }
         if (tstep == 1)

@@ -184,6 +184,15 @@ int cb_module_kernel_info(cb_module m, const char *kernel, int block_threads,
     return CB_OK;
 }
 
+int cb_module_kernel_local_bytes(cb_module m, const char *kernel, int *local_bytes) {
+    CB_REQUIRE(m && kernel && local_bytes, "null argument");
+    CUfunction f;
+    int rc = module_function(m, kernel, &f);
+    if (rc != CB_OK) return rc;
+    CB_DRV(g_drv.FuncGetAttribute(local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f));
+    return CB_OK;
+}
+
 int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,
                      int bx, int by, int bz, int dyn_smem, void **args,
                      cb_stream s) {

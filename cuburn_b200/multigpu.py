@@ -313,11 +313,12 @@ class SharedFrame(object):
             os.unlink(self.path)            # the mappings keep the segment alive
 
     def close(self):
+        """Unpin the frame; the mapping itself goes away with its last numpy view."""
         from . import _native as N
         if self.array is not None:
             N.check(N.lib().cb_host_unregister(self.array.ctypes.data))
             self.array = None
-            self._mm.close()
+            self._mm = None
 
 
 def gather_host_bands(frame, rank, world, root=0):

@@ -215,6 +215,14 @@ class Renderer(object):
                 hot_bins=False):
         pk, src = itergen.mkiterlib(gnm, params_const, acc_packed, hot_bins)
         mod = cls._module(src)
+        if not params_const and not hot_bins and N._initialised is not None \
+                and mod.local_bytes('cb_iter') > 0:
+            # The motion-blur variant of a heavy genome spills at 32 registers (eight CTAs
+            # per SM): six CTAs of 40 registers are faster there (G24H 13.9 -> 12.1 ms,
+            # profiles/r02_iter_variants.md); light genomes keep eight.
+            src = itergen.generate_source(pk, params_const, acc_packed=acc_packed,
+                                          extra_defines={'ITER_MIN_CTAS': '6'})
+            mod = cls._module(src)
         if keep:
             import os, tempfile
             base = os.path.join(tempfile.gettempdir(), 'iter_kern')

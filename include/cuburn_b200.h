@@ -131,6 +131,9 @@ int cb_module_get_cubin(cb_module m, const void **cubin, size_t *size);
 /* registers / static shared memory / max resident CTAs per SM of a kernel */
 int cb_module_kernel_info(cb_module m, const char *kernel, int block_threads,
                           int *num_regs, int *static_smem, int *ctas_per_sm);
+/* Bytes of local memory per thread (register spills, stack): the renderer lowers the
+ * occupancy target of a module whose kernel spills at 32 registers. */
+int cb_module_kernel_local_bytes(cb_module m, const char *kernel, int *local_bytes);
 /* Generic launch of a kernel of a built module: args is an array of pointers
  * to the argument values (cuLaunchKernel convention). */
 int cb_module_launch(cb_module m, const char *kernel, int gx, int gy, int gz,

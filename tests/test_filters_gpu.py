@@ -212,7 +212,14 @@ def test_tile_kernel_equals_the_window_kernel_on_the_transposed_field(native, bu
                                                N.byref(dim), None))
         N.check(N.lib().cb_device_sync())
         return N.from_device(out, field.shape, np.float32)
-    got = run(f, pattern)
+    import os
+    os.environ['CB_BILAT_TILE'] = '1'           # small planes default to the per-pixel kernel
+    try:
+        got = run(f, pattern)
+    finally:
+        del os.environ['CB_BILAT_TILE']
+    untiled = run(f, pattern)
+    assert np.abs(got - untiled).max() <= 2e-6 * float(np.abs(untiled).max())
     want = run(np.ascontiguousarray(f.transpose(1, 0, 2)), twin).transpose(1, 0, 2)
     assert np.isfinite(got).all() and got[..., 3].max() > 1
     scale = float(np.abs(want).max())

@@ -31,7 +31,7 @@ def run(gname, w, h, spp, seed=7, save=None, oracle=True):
     if oracle:
         ev = R.GenomeEval(gnm, w, h, tc, td)
         bad = 0
-        for i, name in enumerate(pk.slot_names):
+        for i, name in pk.named_slots():
             a, b = params[:, i], ev.values[name]
             if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
                 bad += 1
