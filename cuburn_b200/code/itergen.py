@@ -59,42 +59,44 @@ class _Params(object):
         return 'q%d.%s' % (k, 'xyzw'[slot % 4])
 
 
-def _affine_lines(packer, prm, apath, src_x, src_y, dst_x, dst_y):
-    L = []
-    s = {c: prm.ref(packer.slot(apath + (c,)), L) for c in AFFINE_COEFS}
-    return L + [
-        '    %s = %s * %s + %s * %s + %s;' % (dst_x, s['xx'], src_x, s['xy'], src_y, s['xo']),
-        '    %s = %s * %s + %s * %s + %s;' % (dst_y, s['yx'], src_x, s['yy'], src_y, s['yo']),
+def _affine_lines(packer, prm, decl, apath, src_x, src_y, dst_x, dst_y):
+    s = {c: prm.ref(packer.slot(apath + (c,)), decl) for c in AFFINE_COEFS}
+    return [
+        '        %s = %s * %s + %s * %s + %s;' % (dst_x, s['xx'], src_x, s['xy'], src_y, s['xo']),
+        '        %s = %s * %s + %s * %s + %s;' % (dst_y, s['yx'], src_x, s['yy'], src_y, s['yo']),
     ]
 
 
 def _xform_function(packer, fname, xpath, variations, has_post, vector=False):
+    """``void fname(point_set &pt, mwc_st &rng)``: the xform applied to every point of the
+    thread.  Parameter fetches (``decl``) come first and are shared by all points."""
     prm = _Params(vector)
-    L = ['__device__ __forceinline__ void %s(float &x, float &y, '
-         'float &color, mwc_st &rng) {' % fname,
-         '    float tx, ty;']
-    L += _affine_lines(packer, prm, xpath + ('pre_affine',), 'x', 'y', 'tx', 'ty')
-    L.append('    float ox = 0.0f, oy = 0.0f;')
+    decl, body = [], ['        float x = pt.x[p], y = pt.y[p], color = pt.c[p];',
+                      '        float tx, ty;']
+    body += _affine_lines(packer, prm, decl, xpath + ('pre_affine',), 'x', 'y', 'tx', 'ty')
+    body.append('        float ox = 0.0f, oy = 0.0f;')
     # variations in sorted-name order (use.py:90-91, iter.py:132-137)
     for v in variations:
         vpath = xpath + ('variations', v)
-        args = ['tx', 'ty', prm.ref(packer.slot(vpath + ('weight',)), L), 'ox', 'oy']
+        args = ['tx', 'ty', prm.ref(packer.slot(vpath + ('weight',)), decl), 'ox', 'oy']
         if varlib.uses_rng(v):
             args.append('rng')
         for kind, name in varlib.var_args(v):
             if kind == 'pre':
-                args.append(prm.ref(packer.slot(xpath + ('pre_affine', name)), L))
+                args.append(prm.ref(packer.slot(xpath + ('pre_affine', name)), decl))
             else:
-                args.append(prm.ref(packer.slot(vpath + (name,)), L))
-        L.append('    var_%s(%s);' % (v, ', '.join(args)))
+                args.append(prm.ref(packer.slot(vpath + (name,)), decl))
+        body.append('        var_%s(%s);' % (v, ', '.join(args)))
     if has_post:
-        L.append('    tx = ox; ty = oy;')
-        L += _affine_lines(packer, prm, xpath + ('post_affine',), 'tx', 'ty', 'ox', 'oy')
-    L.append('    x = ox; y = oy;')
-    L.append('    float csp = %s;' % prm.ref(packer.slot(xpath + ('color_speed',)), L))
-    L.append('    color = color * (1.0f - csp) + %s * csp;'
-             % prm.ref(packer.slot(xpath + ('color',)), L))
-    L.append('}')
+        body.append('        tx = ox; ty = oy;')
+        body += _affine_lines(packer, prm, decl, xpath + ('post_affine',), 'tx', 'ty', 'ox', 'oy')
+    body.append('        const float csp = %s;' % prm.ref(packer.slot(xpath + ('color_speed',)), decl))
+    body.append('        pt.x[p] = ox; pt.y[p] = oy;')
+    body.append('        pt.c[p] = color * (1.0f - csp) + %s * csp;'
+                % prm.ref(packer.slot(xpath + ('color',)), decl))
+    L = ['__device__ __forceinline__ void %s(point_set &pt, mwc_st &rng) {' % fname]
+    L += decl
+    L += ['#pragma unroll', '    for (int p = 0; p < POINTS; p++) {'] + body + ['    }', '}']
     return '\n'.join(L)
 
 
@@ -109,14 +111,14 @@ def _choice_chain(packer, prm, names, den_slot, indent, xaos):
             head = '%sif (sel <= %s) {' % ('else ' if i else '', refs[i])
         else:
             head = 'else {' if len(names) > 1 else '{'
-        body = ' %s(x, y, color, rng);' % fname
+        body = ' %s(pt, rng);' % fname
         if xpath in packer.opacity:
             OL = []
             op = _Params(prm.vector).ref(packer.opacity[xpath], OL)
             body += ''.join(' ' + l.strip() for l in OL)
-            body += ' vis = opacity_visible(%s, rng);' % op
+            body += (' for (int p = 0; p < POINTS; p++) vis[p] = opacity_visible(%s, rng);' % op)
         if xaos:
-            body += ' last = %d;' % i
+            body += ' pt.last[0] = %d;' % i
         L.append('%s%s%s }' % (indent, head, body))
     return L
 
@@ -133,21 +135,30 @@ def is_heavy(packer):
 
 
 def generate_source(packer, params_const=False, extra_defines=None, acc_packed=False,
-                    hot_bins=False):
+                    hot_bins=False, points=1):
     """
     CUDA source of the iterate module for ``packer``'s genome structure.
     ``params_const`` selects the variant whose parameter block lives in
     __constant__ memory (one block per launch: stills) instead of shared memory;
     ``acc_packed`` the packed-u64 accumulation; ``hot_bins`` the variant that keeps
-    private shared-memory cells for the bins listed in ``iter_args::hot_tags``.
+    private shared-memory cells for the bins listed in ``iter_args::hot_tags``;
+    ``points`` the number of trajectories a thread carries (xaos genomes: always 1).
     """
     extra_defines = dict(extra_defines or {})
     vector = (not params_const) and extra_defines.pop('PARAMS_VECTOR', '1') != '0'
+    points = 1 if packer.xaos else int(extra_defines.pop('POINTS', points))
     out = ['// generated by cuburn_b200.code.itergen -- do not edit']
     for k, v in extra_defines.items():
         out.append('#define %s %s' % (k, v))
+    if not params_const and 'ITER_MIN_CTAS' not in extra_defines:
+        # Motion blur: the parameter block lives in shared memory and every value read
+        # from it needs a register; six CTAs of 40 registers beat eight of 32 (G24H, which
+        # spills at 32: 12.3 -> 11.1 ms; G6F 27.4 -> 26.6; G3 unchanged --
+        # profiles/r02_iter_variants.md)
+        out.append('#define ITER_MIN_CTAS 6')
     out += ['#include "mwc.cuh"', '#include "variations.cuh"', '']
     out.append('#define NSLOTS %d' % packer.nslots)
+    out.append('#define POINTS %d' % points)
     out.append('#define PARAMS_CONST %d' % (1 if params_const else 0))
     out.append('#define ACC_PACKED %d' % (1 if acc_packed else 0))
     out.append('#define HOT_BINS %d' % (1 if hot_bins else 0))
@@ -168,12 +179,12 @@ def generate_source(packer, params_const=False, extra_defines=None, acc_packed=F
         out.append(_xform_function(packer, fname, xpath, variations, has_post, vector))
         out.append('')
 
-    L = ['__device__ __forceinline__ bool chaos_step(float sel, float &x, float &y, '
-         'float &color, int &last, mwc_st &rng) {',
-         '    bool vis = true;']
+    L = ['__device__ __forceinline__ void chaos_step(float sel, point_set &pt, mwc_st &rng, '
+         'bool (&vis)[POINTS]) {',
+         '    for (int p = 0; p < POINTS; p++) vis[p] = true;']
     ids = [xpath[1] for _, xpath in names]
     if packer.xaos:
-        L.append('    switch (last) {')
+        L.append('    switch (pt.last[0]) {')
         for p, pid in enumerate(ids):
             prm = _Params(vector)
             L.append('    %s: {' % ('default' if p == len(ids) - 1 else 'case %d' % p))
@@ -186,14 +197,12 @@ def generate_source(packer, params_const=False, extra_defines=None, acc_packed=F
         prm = _Params(vector)
         L += _choice_chain(packer, prm, names,
                            lambda i: packer.slot(('xforms', ids[i], 'density')), '    ', False)
-    L.append('    return vis;')
     L.append('}')
     out.append('\n'.join(L))
     out.append('')
     if packer.has_final:
-        out.append('__device__ __forceinline__ void final_step(float &x, '
-                   'float &y, float &color, mwc_st &rng) {\n'
-                   '    apply_xf_final(x, y, color, rng);\n}')
+        out.append('__device__ __forceinline__ void final_step(point_set &pt, mwc_st &rng) {\n'
+                   '    apply_xf_final(pt, rng);\n}')
         out.append('')
     # camera affine (iter.py:302-311) as six named coefficients
     prm, CL = _Params(vector), []
@@ -205,8 +214,13 @@ def generate_source(packer, params_const=False, extra_defines=None, acc_packed=F
     return '\n'.join(out) + '\n'
 
 
-def mkiterlib(gnm, params_const=False, acc_packed=False, hot_bins=False):
+def mkiterlib(gnm, params_const=False, acc_packed=False, hot_bins=False, points=1):
     """``(packer, source)`` for a genome (mirrors iter.mkiterlib, iter.py:559-575)."""
     packer = GenomePacker(gnm)
     return packer, generate_source(packer, params_const, acc_packed=acc_packed,
-                                   hot_bins=hot_bins)
+                                   hot_bins=hot_bins, points=points)
+
+
+def points_per_thread(packer, points):
+    """Trajectories per thread a module built with ``points`` really uses."""
+    return 1 if packer.xaos else points

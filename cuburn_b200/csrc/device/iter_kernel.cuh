@@ -9,13 +9,17 @@
 //                            identical); parameters become constant-bank operands
 //                         0: the block of the unit's temporal sample is staged in
 //                            shared memory (motion blur)
-//   bool chaos_step(float sel, float &x, float &y, float &c, int &last, mwc_st &rng)
-//                         the weighted xform choice + application; reads P[slot];
-//                         returns whether the new point is visible (xform opacity,
-//                         genome/specs.py:17); `last` is the index of the xform the
-//                         point went through before (only read when XAOS) and is
-//                         updated
-//   void final_step(float &x, float &y, float &c, mwc_st &rng)   (if HAS_FINAL)
+//   POINTS                points per thread (1 or 2): a thread carries POINTS trajectories
+//                         through every round, all through the xform its warp chose, so
+//                         that the choice, the parameter fetches and the loop overhead
+//                         are paid once per POINTS samples
+//   void chaos_step(float sel, point_set &pt, mwc_st &rng, bool (&vis)[POINTS])
+//                         the weighted xform choice + application to all points of the
+//                         thread; reads P[slot]; vis[p]: whether the new point is visible
+//                         (xform opacity, genome/specs.py:17); pt.last[p] is the index of
+//                         the xform the point went through before (only read when XAOS)
+//                         and is updated
+//   void final_step(point_set &pt, mwc_st &rng)   (if HAS_FINAL)
 //   XAOS                  0/1: xform choice depends on the previous xform of the
 //                         trajectory (iter.py:32-54,233-257); as in the reference the
 //                         choice is then per thread and points are not exchanged
@@ -101,6 +105,11 @@ struct iter_args {
 
 #define ITER_WARPS (ITER_THREADS / 32)
 #define UNIT_SAMPLES (ITER_THREADS * UNIT_ROUNDS)
+#if XAOS && POINTS != 1
+#error "xaos chooses per point: POINTS must be 1"
+#endif
+// iter_args::points holds POINTS planes of this many trajectories (= RNG streams)
+#define POINT_STRIDE 262144
 
 __device__ __forceinline__ void red_add_f32x4(float4 *addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -182,8 +191,8 @@ __device__ __forceinline__ unsigned int color_index(float color, float dither) {
 // permuted write and the linear read are bank-conflict free (64-bit accesses are
 // served per half-warp; the lane permutation below is a bijection mod 16).
 struct xchg_buf {
-    float2 xy[ITER_THREADS];
-    float c[ITER_THREADS];
+    float2 xy[POINTS * ITER_THREADS];
+    float c[POINTS * ITER_THREADS];
 };
 
 #ifndef XCHG_MODE
@@ -258,14 +267,16 @@ __device__ __forceinline__ void hot_flush(hot_table *ht, const iter_args &a, int
 // warp's random word (its low bits pick the lane that drains packed cells); `visible`
 // says whether the new point may be recorded (xform opacity).
 __device__ __forceinline__ unsigned int chaos_push(xchg_buf *xb, int tid, int warp, int lane, int round,
-                                                   float &x, float &y, float &c, int &last,
-                                                   mwc_st &rng, bool &visible) {
-    if (point_is_bad(x, y)) reseed_point(x, y, c, rng);
+                                                   point_set &pt, mwc_st &rng,
+                                                   bool (&visible)[POINTS]) {
+#pragma unroll
+    for (int p = 0; p < POINTS; p++)
+        if (point_is_bad(pt.x[p], pt.y[p])) reseed_point(pt.x[p], pt.y[p], pt.c[p], rng);
 
 #if XAOS
     // the choice depends on the trajectory's previous xform: one random per thread,
     // and the point stays with its thread (iter.py:236-257)
-    visible = chaos_step(mwc_next_01(rng), x, y, c, last, rng);
+    chaos_step(mwc_next_01(rng), pt, rng, visible);
     return (unsigned int)round;
 #else
     // one random word per warp per round (iter.py:197-201,261)
@@ -273,25 +284,33 @@ __device__ __forceinline__ unsigned int chaos_push(xchg_buf *xb, int tid, int wa
     if (lane == 0) word = mwc_next(rng);
     word = __shfl_sync(0xffffffffu, word, 0);
     float sel = __uint2float_rn(word) * 2.3283064365386962890625e-10f;
-    visible = chaos_step(sel, x, y, c, last, rng);
+    chaos_step(sel, pt, rng, visible);
 
     xchg_buf *b = xb + (round & 1);
-    int slot = exchange_slot(tid, warp, lane, round);
-    b->xy[slot] = make_float2(x, y);
-    b->c[slot] = c;
+#pragma unroll
+    for (int p = 0; p < POINTS; p++) {
+        // the thread's p-th points circulate among the p-th points of the CTA, each
+        // population under its own sequence of permutations
+        int slot = p * ITER_THREADS + exchange_slot(tid, warp, lane, POINTS * round + p);
+        b->xy[slot] = make_float2(pt.x[p], pt.y[p]);
+        b->c[slot] = pt.c[p];
+    }
     return word;
 #endif
 }
 
-// Second half: take the point another thread published this round.
-__device__ __forceinline__ void chaos_pull(xchg_buf *xb, int tid, int round, float &x, float &y, float &c) {
+// Second half: take the points other threads published this round.
+__device__ __forceinline__ void chaos_pull(xchg_buf *xb, int tid, int round, point_set &pt) {
 #if !XAOS
     __syncthreads();
     xchg_buf *b = xb + (round & 1);
-    float2 p = b->xy[tid];
-    x = p.x;
-    y = p.y;
-    c = b->c[tid];
+#pragma unroll
+    for (int p = 0; p < POINTS; p++) {
+        float2 q = b->xy[p * ITER_THREADS + tid];
+        pt.x[p] = q.x;
+        pt.y[p] = q.y;
+        pt.c[p] = b->c[p * ITER_THREADS + tid];
+    }
 #endif
 }
 
@@ -364,8 +383,7 @@ cb_iter(const __grid_constant__ iter_args a) {
     const int gtid = blockIdx.x * ITER_THREADS + tid;
 
     mwc_st rng = a.seeds[gtid];
-    float x, y, c;
-    int last = 0;               // iter.py:209
+    point_set pt;
 
     const unsigned long long unit0 = a.first_sample / UNIT_SAMPLES;
     const unsigned long long nunits = (a.nsamples + UNIT_SAMPLES - 1) / UNIT_SAMPLES;
@@ -375,11 +393,15 @@ cb_iter(const __grid_constant__ iter_args a) {
     int round_ctr = a.first_round;
     int cur_row = -1;
     bool fresh = a.fuse_rounds > 0;
-    if (fresh) {
-        reseed_point(x, y, c, rng);
-    } else {
-        float4 p = a.points[gtid];
-        x = p.x; y = p.y; c = p.z;
+#pragma unroll
+    for (int p = 0; p < POINTS; p++) {
+        pt.last[p] = 0;               // iter.py:209
+        if (fresh) {
+            reseed_point(pt.x[p], pt.y[p], pt.c[p], rng);
+        } else {
+            float4 q = a.points[p * POINT_STRIDE + gtid];
+            pt.x[p] = q.x; pt.y[p] = q.y; pt.c[p] = q.z;
+        }
     }
 #if HOT_BINS
     for (int s = tid; s < HOT_SLOTS; s += ITER_THREADS) {
@@ -418,46 +440,55 @@ cb_iter(const __grid_constant__ iter_args a) {
 
         if (fresh) {
             // settle new trajectories without recording them (iter.py:211-216)
-            bool vis;
+            bool vis[POINTS];
             for (int r = 0; r < a.fuse_rounds; r++, round_ctr++) {
-                chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, last, rng, vis);
-                chaos_pull(xb, tid, round_ctr, x, y, c);
+                chaos_push(xb, tid, warp, lane, round_ctr, pt, rng, vis);
+                chaos_pull(xb, tid, round_ctr, pt);
             }
             fresh = false;
             if (lu >= nunits) break;
         }
 
-        // samples of this unit that belong to the request
+        // samples of this unit that belong to the request: round r of the unit produces
+        // samples (r * POINTS + p) * ITER_THREADS + tid
         unsigned long long done = lu * UNIT_SAMPLES;
         unsigned long long left = a.nsamples - done;
         int live = left >= UNIT_SAMPLES ? UNIT_SAMPLES : (int)left;
-        int rounds = (live + ITER_THREADS - 1) / ITER_THREADS;
+        int rounds = (live + POINTS * ITER_THREADS - 1) / (POINTS * ITER_THREADS);
 
         const float color_dither = 0.49f * mwc_next_11(rng);      // iter.py:185
 
         for (int r = 0; r < rounds; r++, round_ctr++) {
-            bool visible;
-            unsigned int word = chaos_push(xb, tid, warp, lane, round_ctr, x, y, c, last, rng,
-                                           visible);
-            // The sample of the point this thread just produced.  Its coordinates are
-            // dead once published (the thread continues with the point it receives), so
-            // the final xform and the camera run with x, y, c off the register file.
-            int bin = -1;
-            unsigned int cidx = 0;
-            if (visible && r * ITER_THREADS + tid < live) {
-                float fx = x, fy = y, fc = c;
+            bool visible[POINTS];
+            unsigned int word = chaos_push(xb, tid, warp, lane, round_ctr, pt, rng, visible);
+            // The samples of the points this thread just produced.  Their coordinates are
+            // dead once published (the thread continues with the points it receives), so
+            // the final xform and the camera run with them off the register file.
+            int bin[POINTS];
+            unsigned int cidx[POINTS];
+            point_set f = pt;
 #if HAS_FINAL
-                final_step(fx, fy, fc, rng);
+            final_step(f, rng);
 #endif
-                bin = sample_bin(fx, fy, a.dim.astride, a.dim.aheight);
-                cidx = color_index(fc, color_dither);
+#pragma unroll
+            for (int p = 0; p < POINTS; p++) {
+                bin[p] = -1;
+                cidx[p] = 0;
+                if (visible[p] && (r * POINTS + p) * ITER_THREADS + tid < live) {
+                    bin[p] = sample_bin(f.x[p], f.y[p], a.dim.astride, a.dim.aheight);
+                    cidx[p] = color_index(f.c[p], color_dither);
+                }
             }
 #if RED_BEFORE_PULL
-            if (bin >= 0) record_sample(a, sm, bin, cidx, word, lane);
-            chaos_pull(xb, tid, round_ctr, x, y, c);
+#pragma unroll
+            for (int p = 0; p < POINTS; p++)
+                if (bin[p] >= 0) record_sample(a, sm, bin[p], cidx[p], word, lane);
+            chaos_pull(xb, tid, round_ctr, pt);
 #else
-            chaos_pull(xb, tid, round_ctr, x, y, c);
-            if (bin >= 0) record_sample(a, sm, bin, cidx, word, lane);
+            chaos_pull(xb, tid, round_ctr, pt);
+#pragma unroll
+            for (int p = 0; p < POINTS; p++)
+                if (bin[p] >= 0) record_sample(a, sm, bin[p], cidx[p], word, lane);
 #endif
         }
     }
@@ -466,7 +497,9 @@ cb_iter(const __grid_constant__ iter_args a) {
     hot_flush(&sm.hot, a, tid);
 #endif
 
-    a.points[gtid] = make_float4(x, y, c, 0.0f);
+#pragma unroll
+    for (int p = 0; p < POINTS; p++)
+        a.points[p * POINT_STRIDE + gtid] = make_float4(pt.x[p], pt.y[p], pt.c[p], 0.0f);
     a.seeds[gtid] = rng;
 }
 
@@ -486,18 +519,19 @@ extern "C" __global__ void cb_probe_xform(const float *params, float *xs, float 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     mwc_st rng = seeds[i];
-    float x = xs[i], y = ys[i], c = cs[i];
+    point_set pt;               // the probes are built with POINTS == 1
+    pt.x[0] = xs[i]; pt.y[0] = ys[i]; pt.c[0] = cs[i]; pt.last[0] = last_xf;
 #if HAS_FINAL
-    if (use_final) final_step(x, y, c, rng);
+    if (use_final) final_step(pt, rng);
     else
 #endif
     {
-        int last = last_xf;
-        bool vis = chaos_step(sel, x, y, c, last, rng);
-        if (visible) visible[i] = vis ? 1 : 0;
-        if (last_out) last_out[i] = last;
+        bool vis[POINTS];
+        chaos_step(sel, pt, rng, vis);
+        if (visible) visible[i] = vis[0] ? 1 : 0;
+        if (last_out) last_out[i] = pt.last[0];
     }
-    xs[i] = x; ys[i] = y; cs[i] = c;
+    xs[i] = pt.x[0]; ys[i] = pt.y[0]; cs[i] = pt.c[0];
     seeds[i] = rng;
 }
 

@@ -13,6 +13,15 @@
 #define ITER_MIN_CTAS 8        // 32 registers, 64 warps / SM: measured fastest (profiles/r01_iter_variants.md)
 #endif
 
+#ifndef POINTS
+#define POINTS 1
+#endif
+// The trajectories one thread carries through a round.
+struct point_set {
+    float x[POINTS], y[POINTS], c[POINTS];
+    int last[POINTS];           // previous xform of each trajectory (xaos)
+};
+
 #if PARAMS_CONST
 // Stills: one block for the whole launch.  Constant indices make every P[slot] a
 // constant-bank operand of the consuming instruction (no load, no register).

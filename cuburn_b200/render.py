@@ -73,7 +73,8 @@ class Framebuffers(object):
         self._clear()
         seeds = mwc.make_seeds(self.nstreams, host_seed=seed)
         self.d_seeds = N.to_device(seeds)
-        self._len_d_points = self.nstreams * 16
+        # two trajectories per RNG stream (the iterate kernel's POINTS)
+        self._len_d_points = 2 * self.nstreams * 16
         self.d_points = N.DeviceBuffer(self._len_d_points)
         N.fill32(self.d_points, self._len_d_points // 4, np.float32(np.nan))
         N.check(N.lib().cb_device_sync())
@@ -198,6 +199,10 @@ class Renderer(object):
     """
     MAX_MODREFS = 40
     _modrefs = {}
+    # trajectories per thread of the production modules (1 for xaos genomes): the xform
+    # choice, the parameter fetches and the loop overhead are paid once per `points`
+    # samples (profiles/r02_iter_variants.md)
+    points = 2
 
     @classmethod
     def _module(cls, src):
@@ -213,16 +218,8 @@ class Renderer(object):
     @classmethod
     def compile(cls, gnm, arch=None, keep=False, params_const=False, acc_packed=False,
                 hot_bins=False):
-        pk, src = itergen.mkiterlib(gnm, params_const, acc_packed, hot_bins)
+        pk, src = itergen.mkiterlib(gnm, params_const, acc_packed, hot_bins, points=cls.points)
         mod = cls._module(src)
-        if not params_const and not hot_bins and N._initialised is not None \
-                and mod.local_bytes('cb_iter') > 0:
-            # The motion-blur variant of a heavy genome spills at 32 registers (eight CTAs
-            # per SM): six CTAs of 40 registers are faster there (G24H 13.9 -> 12.1 ms,
-            # profiles/r02_iter_variants.md); light genomes keep eight.
-            src = itergen.generate_source(pk, params_const, acc_packed=acc_packed,
-                                          extra_defines={'ITER_MIN_CTAS': '6'})
-            mod = cls._module(src)
         if keep:
             import os, tempfile
             base = os.path.join(tempfile.gettempdir(), 'iter_kern')
@@ -482,7 +479,9 @@ class RenderManager(object):
                 hot = rdr.hot = bool(probe[0] > 0)
                 probe = None
             # the pilot is whole waves: every CTA has run the same number of rounds
-            first_round = fuse + (npilot // UNIT_SAMPLES // grid) * (UNIT_SAMPLES // ITER_THREADS)
+            ppt = itergen.points_per_thread(rdr.packer, rdr.points)
+            first_round = fuse + (npilot // UNIT_SAMPLES // grid) * \
+                (UNIT_SAMPLES // (ITER_THREADS * ppt))
             first, n, fuse = first + npilot, n - npilot, 0
         if hot:
             mod = rdr.variant(still, packed, True)

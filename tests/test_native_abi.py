@@ -92,11 +92,20 @@ def test_nvrtc_compiles_every_variation(built):
 
 def test_sample_genome_modules_use_vector_red(built, tmp_path):
     """SASS evidence: 16-byte float4 reductions and SFU intrinsics; the 32-register
-    cap (64 warps/SM, measured fastest) may cost a few bytes of spill, no more."""
+    cap of the still variant (64 warps/SM, measured fastest) may cost a few bytes of
+    spill, no more; the motion-blur variant runs six CTAs of at most 40 registers."""
     from cuburn_b200 import _native as N, samples
     from cuburn_b200.code import itergen
     hn, hs = itergen.load_headers()
     pk, src = itergen.mkiterlib(samples.g6f())
+    blur = N.Module(src, 'g6f_blur.cu', hs, hn, itergen.NVRTC_OPTIONS)
+    pb = tmp_path / 'g6f_blur.cubin'
+    pb.write_bytes(blur.cubin)
+    usage = subprocess.run(['cuobjdump', '-res-usage', str(pb)], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True).stdout
+    m = re.search(r'Function cb_iter:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)', usage)
+    assert m and int(m.group(1)) <= 40 and int(m.group(2)) == 0 and int(m.group(4)) == 0
+    pk, src = itergen.mkiterlib(samples.g6f(), params_const=True)
     mod = N.Module(src, 'g6f.cu', hs, hn, itergen.NVRTC_OPTIONS)
     p = tmp_path / 'g6f.cubin'
     p.write_bytes(mod.cubin)
