@@ -224,3 +224,24 @@ def mkiterlib(gnm, params_const=False, acc_packed=False, hot_bins=False, points=
 def points_per_thread(packer, points):
     """Trajectories per thread a module built with ``points`` really uses."""
     return 1 if packer.xaos else points
+
+
+def best_points(packer, params_const):
+    """
+    Trajectories per thread of the production module.  Two points per thread share the
+    xform choice, the parameter fetches and the loop overhead.  Measured on B200
+    (profiles/r02_iter_variants.md, 1080p, ms per frame, one / two points):
+
+                          G3 (5 variation uses)   G6F (16)        G24H (72)
+        still             20.9 / 24.2             24.0 / 23.6     11.7 / 15.8
+        motion blur       21.6 / 24.5             27.1 / 24.7     12.4 / 16.5
+
+    It pays where the kernel is bound by shared-memory parameter fetches (motion blur
+    of a mid-sized genome: -9 %, which brings the blurred frame within 3 % of the still),
+    does nothing for stills (parameters are constant-bank operands there), hurts light
+    genomes (their warps run in lockstep and the doubled burst of reductions after each
+    barrier stalls them) and heavy ones (twice the code no longer fits the instruction
+    cache).
+    """
+    uses = sum(len(variations) for _, variations, _ in packer.xforms)
+    return 2 if (not params_const and not packer.xaos and 12 <= uses <= 32) else 1

@@ -79,15 +79,16 @@ class Bilateral(Filter):
     def apply(self, fb, gprof, params, dim, tc, stream=None):
         L, s = N.lib(), _h(stream)
         coefs = gauss_coefs(1)
+        # a "pixel" of spatial_std means a 1080p pixel (filters.py:74-76)
+        sstd = f32(params.spatial_std(tc) * dim.w / 1920.)
+        cstd, dstd = f32(params.color_std(tc)), f32(params.density_std(tc))
+        dpow, grad = f32(params.density_pow(tc)), f32(params.gradient(tc))
         for pattern in range(self.directions):
-            # a "pixel" of spatial_std means a 1080p pixel (filters.py:74-76)
-            sstd = params.spatial_std(tc) * dim.w / 1920.
             # den_blur -> den_blur_1c -> bilateral of the reference recipe
             # (filters.py:80-94), fused into one restructured direction pass
             N.check(L.cb_bilateral_direction(
                 fb.d_back.ptr, fb.d_front.ptr, fb.d_left.ptr, pattern, self.radius, coefs,
-                f32(sstd), f32(params.color_std(tc)), f32(params.density_std(tc)),
-                f32(params.density_pow(tc)), f32(params.gradient(tc)), N.byref(dim), s))
+                sstd, cstd, dstd, dpow, grad, N.byref(dim), s))
             fb.flip()
 
     def reach(self, gprof, params, tc):

@@ -170,18 +170,24 @@ class SplineEval(object):
         scale = 1.0 / times[2]
         return times * scale, vals, t * scale, scale
 
+    # Hermite basis as polynomials in t (highest power first) and their derivatives;
+    # evaluated with Horner's rule in plain floats (this runs ~50 times per frame on the
+    # host: filter parameters, spp, frame width)
+    _BASIS = [[list(np.poly1d(c).deriv(k).coeffs) if k else list(c) for c in
+               ([1., -2, 1, 0], [2., -3, 0, 1], [1., -1, 0, 0], [-2., 3, 0, 0])]
+              for k in range(4)]
+
     def __call__(self, itime, deriv=0):
         times, vals, t, scale = self.find_knots(itime)
         m1 = (vals[2] - vals[0]) / (1.0 - times[0])
         m2 = (vals[3] - vals[1]) / times[3]
-        # Hermite basis as polynomials in t, highest power first.
-        basis = [np.poly1d([1., -2, 1, 0]), np.poly1d([2., -3, 0, 1]),
-                 np.poly1d([1., -1, 0, 0]), np.poly1d([-2., 3, 0, 0])]
+        t, mult = float(t), float(scale) ** deriv if deriv else 1.0
         total = 0.0
-        for coef, b in zip((m1, vals[1], m2, vals[2]), basis):
-            if deriv:
-                b = b.deriv(deriv) * (scale ** deriv)
-            total += coef * b(t)
+        for coef, poly in zip((m1, vals[1], m2, vals[2]), self._BASIS[deriv]):
+            acc = 0.0
+            for c in poly:
+                acc = acc * t + (c * mult if deriv else c)
+            total += float(coef) * acc
         return float(total)
 
     def __imul__(self, other):

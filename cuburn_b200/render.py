@@ -199,10 +199,9 @@ class Renderer(object):
     """
     MAX_MODREFS = 40
     _modrefs = {}
-    # trajectories per thread of the production modules (1 for xaos genomes): the xform
-    # choice, the parameter fetches and the loop overhead are paid once per `points`
-    # samples (profiles/r02_iter_variants.md)
-    points = 2
+    # trajectories per thread of the production modules: None = itergen.best_points
+    # (two for the motion-blur variant of mid-sized genomes, else one)
+    points = None
 
     @classmethod
     def _module(cls, src):
@@ -216,9 +215,15 @@ class Renderer(object):
         return mod
 
     @classmethod
+    def _points(cls, pk, params_const):
+        return cls.points if cls.points is not None else itergen.best_points(pk, params_const)
+
+    @classmethod
     def compile(cls, gnm, arch=None, keep=False, params_const=False, acc_packed=False,
                 hot_bins=False):
-        pk, src = itergen.mkiterlib(gnm, params_const, acc_packed, hot_bins, points=cls.points)
+        pk = itergen.GenomePacker(gnm)
+        src = itergen.generate_source(pk, params_const, acc_packed=acc_packed, hot_bins=hot_bins,
+                                      points=cls._points(pk, params_const))
         mod = cls._module(src)
         if keep:
             import os, tempfile
@@ -479,7 +484,7 @@ class RenderManager(object):
                 hot = rdr.hot = bool(probe[0] > 0)
                 probe = None
             # the pilot is whole waves: every CTA has run the same number of rounds
-            ppt = itergen.points_per_thread(rdr.packer, rdr.points)
+            ppt = itergen.points_per_thread(rdr.packer, rdr._points(rdr.packer, still))
             first_round = fuse + (npilot // UNIT_SAMPLES // grid) * \
                 (UNIT_SAMPLES // (ITER_THREADS * ppt))
             first, n, fuse = first + npilot, n - npilot, 0
