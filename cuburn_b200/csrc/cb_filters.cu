@@ -1235,13 +1235,14 @@ static int bilateral_main(float4 *dst, const float4 *src, const float2 *side, in
     kc.dscale = -0.5f / dstd;
     kc.gspeed = gspeed;
     const dim3 grid(dim->astride / 32, (dim->aheight + 31) / 32);
-    // Measured (profiles/r02_filter_kernels.md): the staged tile wins once a plane no longer
-    // fits L2 (4K: 380 vs 436 us for (1,0)); at 1080p the one-pixel-per-thread kernel,
+    // Measured (profiles/r02_filter_kernels.md): the staged tile wins on 4K-wide frames, whose
+    // planes no longer fit L2 (375 vs 436 us for (1,0)); at 1080p the one-pixel-per-thread kernel,
     // whose loads overlap its arithmetic, is faster (127 vs 153 us).  CB_BILAT_TILE=0/1
     // forces the choice (tests run both).
     const char *force = getenv("CB_BILAT_TILE");
-    const bool tile = force ? force[0] == '1'
-                            : (size_t)nbins(dim) * sizeof(float4) > ((size_t)96 << 20);
+    // (the width decides, not the plane: a row band of a frame -- multi-GPU stills -- must
+    // run the same kernel as the whole frame to stay bit-identical to it)
+    const bool tile = force ? force[0] == '1' : dim->astride >= 3072;
     if (tstep && tile && dim->astride >= 96) {
         const bilat_tab tab = make_bilat_tab(pattern, tstep, sstd, BT_PITCH4, BT_PITCH2);
         const int nrows = 32 + tab.yhi - tab.ylo;

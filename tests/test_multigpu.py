@@ -329,15 +329,16 @@ def test_frame_seed_keeps_rank_streams_disjoint(native, built):
 
 
 @pytest.mark.gpu
-def test_banded_output_into_a_shared_frame_equals_the_whole_frame(native, built):
+@pytest.mark.parametrize('w,h', [(256, 1000), (3200, 500)])
+def test_banded_output_into_a_shared_frame_equals_the_whole_frame(native, built, w, h):
     """Every rank filters its band, converts its own output rows (cb_convert_rows) and
     copies them into one page-locked shared-memory frame: the assembled frame is
     byte-identical to the frame rendered on one GPU.  One process plays the ranks in
-    turn on the same histogram."""
+    turn on the same histogram.  The wide frame runs the TMA-staged tile kernel for the
+    x-major bilateral directions, in the bands as in the whole frame."""
     N = native
     from cuburn_b200 import samples, render, profile, multigpu
     gnm = samples.g6f()
-    w, h = 256, 1000
     gprof = profile.wrap(dict(width=w, height=h, spp=40, frame_width=0, start=1, end=2), gnm)
     tc = profile.enumerate_times(gprof)[0][1][0]
     rmgr = render.RenderManager(seed=4)
