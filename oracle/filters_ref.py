@@ -108,12 +108,34 @@ def bilateral_pass(pix, pattern, radius, sstd, cstd, dstd, dpow, gspeed):
         return ftz(acc * rcp[..., None])
 
 
+def _in_strips(fn, pix, halo, threads):
+    """Run ``fn`` (a stencil whose result at a row depends on at most ``halo`` rows either
+    side) on horizontal strips in parallel threads; identical to ``fn(pix)``: a strip is
+    cut with its halo, real image borders stay borders (so edge clamping is unchanged)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rows = pix.shape[0]
+    n = max(1, min(threads, rows // (4 * halo)))
+    if n == 1:
+        return fn(pix)
+    edges = [rows * k // n for k in range(n + 1)]
+
+    def job(k):
+        a, b = edges[k], edges[k + 1]
+        lo, hi = max(a - halo, 0), min(b + halo, rows)
+        return fn(pix[lo:hi])[a - lo:a - lo + (b - a)]
+    with ThreadPoolExecutor(n) as pool:
+        return np.concatenate(list(pool.map(job, range(n))), axis=0)
+
+
 def bilateral(pix, w, spatial_std=6, color_std=0.05, density_std=1.5, density_pow=0.8,
-              gradient=4.0, radius=15, directions=8):
+              gradient=4.0, radius=15, directions=8, threads=1):
+    """``threads`` > 1: each direction pass runs on row strips in parallel (same result;
+    a pass reaches radius + 1 taps plus the 6 + 3 rows of the two density blurs)."""
     sstd = spatial_std * w / 1920.
     for pattern in range(directions):
-        pix = bilateral_pass(pix, pattern, radius, sstd, color_std, density_std,
-                             density_pow, gradient)
+        fn = lambda p: bilateral_pass(p, pattern, radius, sstd, color_std, density_std,
+                                      density_pow, gradient)
+        pix = _in_strips(fn, pix, radius + 1 + 9 + 6, threads)
     return pix
 
 
@@ -222,10 +244,10 @@ def logencode(pix, degamma=2.2):
 
 
 def default_chain(hist, w, h, scale, spp, brightness=4, gamma=4, threshold=0.01,
-                  smear_width=0.7):
+                  smear_width=0.7, threads=1):
     """yuv -> bilateral -> logscale -> smearclip, with schema defaults."""
     pix = yuv_to_rgb(hist)
-    pix = bilateral(pix, w)
+    pix = bilateral(pix, w, threads=threads)
     k1, k2 = logscale_consts(brightness, scale, w, h, spp)
     pix = logscale(pix, k1, k2)
     return smearclip(pix, smear_width, gamma, threshold)

@@ -13,14 +13,14 @@ from helpers import still_profile, frame_window, psnr
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_frame(gnm, w, h, spp, tc, td, seed):
+def _oracle_frame(gnm, w, h, spp, tc, td, seed, threads=1):
     from cuburn_b200 import mwc
     from oracle import flame_ref as R, filters_ref as F, output_ref as O
     ev = R.GenomeEval(gnm, w, h, tc, td)
     seeds = mwc.make_seeds(262144, host_seed=seed)
     pal, seeds = R.palette_table(gnm, tc - 0.5 * td, td, seeds)
     hist, _ = R.iterate(ev, pal, seeds, w * h * spp)
-    pix = F.default_chain(hist, w, h, gnm['camera']['scale'], spp)
+    pix = F.default_chain(hist, w, h, gnm['camera']['scale'], spp, threads=threads)
     o8, _ = O.convert('rgba_u8', pix, w, h, seeds)
     return o8.reshape(h, w, 4)
 
@@ -40,6 +40,28 @@ def test_frame_psnr_vs_oracle(native, built, gname, spp):
     assert evt.query() and evt.time() > 0
     want = _oracle_frame(gnm, w, h, spp, tc, 0.0, seed=77)
     assert frame.shape == want.shape == (h, w, 4) and frame.dtype == np.uint8
+    val = psnr(frame[..., :3], want[..., :3])
+    assert val >= 40.0, val
+
+
+def test_frame_psnr_vs_oracle_at_1080p(native, built):
+    """BASELINE config 2 end to end against the oracle at its real size: the 1080p /
+    2000 spp G6F frame through queue_frame (device interpolation, chaos game, filter
+    chain, RGBA8) vs the oracle's chaos game (4.1e9 iterations on the host cores), numpy
+    filter chain (row strips in threads) and output conversion: >= 40 dB."""
+    import os
+    from cuburn_b200 import samples, render
+    gnm = samples.g6f()
+    w, h, spp = 1920, 1080, 2000
+    gprof, tc = still_profile(gnm, w, h, spp)
+    rmgr = render.RenderManager(seed=31)
+    rdr = render.Renderer(gnm, gprof)
+    evt, frame = rmgr.queue_frame(rdr, gnm, gprof, tc)
+    evt.synchronize()
+    frame = np.array(frame)
+    rmgr.fb.free()
+    want = _oracle_frame(gnm, w, h, spp, tc, 0.0, seed=77, threads=os.cpu_count() or 8)
+    assert frame.shape == want.shape == (h, w, 4)
     val = psnr(frame[..., :3], want[..., :3])
     assert val >= 40.0, val
 
