@@ -100,14 +100,19 @@ enum { OP_DIRECT = 0, OP_DIRECT_MAG, OP_AFFINE, OP_CAMERA, OP_DENSITY,
 
 #define DEG2RAD(a) FD(FM((a), 3.14159274101257f), 180.0f)
 
+#define OPS_PER_THREAD 8
 __global__ void __launch_bounds__(128)
 k_interp_params(float *params, int stride, const float *vals, int nrows,
                 const int *prog, int nops, cb_dims dim, int nts) {
+    // one thread per (temporal sample, group of OPS_PER_THREAD ops): ops are independent
+    // (each reads spline rows and writes its own slots)
     int ts = blockIdx.x * blockDim.x + threadIdx.x;
     if (ts >= nts) return;
     const float *v = vals + (size_t)ts * nrows;
     float *out = params + (size_t)ts * stride;
-    for (int o = 0; o < nops; o++) {
+    const int o0 = blockIdx.y * OPS_PER_THREAD;
+    const int o1 = min(o0 + OPS_PER_THREAD, nops);
+    for (int o = o0; o < o1; o++) {
         const int *w = prog + o * PROG_W;
         int op = w[0], dst = w[1];
         const int *in = w + 2;
@@ -273,7 +278,9 @@ int cb_interp_params(cb_dptr params, int param_stride, cb_dptr vals, int nrows,
                      cb_dptr program, int nops, const cb_dims *dim, int nts,
                      cb_stream s) {
     CB_REQUIRE(dim && nts > 0 && nops >= 0, "bad interp_params request");
-    k_interp_params<<<(nts + 127) / 128, 128, 0, cb_cs(s)>>>(
+    if (nops == 0) return CB_OK;
+    const dim3 grid((nts + 127) / 128, (nops + OPS_PER_THREAD - 1) / OPS_PER_THREAD);
+    k_interp_params<<<grid, 128, 0, cb_cs(s)>>>(
         cb_ptr<float>(params), param_stride, cb_ptr<const float>(vals), nrows,
         cb_ptr<const int>(program), nops, *dim, nts);
     CB_LAUNCH_CHECK();
