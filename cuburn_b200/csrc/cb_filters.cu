@@ -444,64 +444,6 @@ k_bilat_prep2(float2 *side, const float2 *aux, int pattern, coefs7 k, cb_dims di
     }
 }
 
-// Both prologues in one launch, through shared memory.  A block of 256 threads produces the
-// records of a 32 x 32 tile: (1) the densities of the tile and 9 bins around it are staged
-// (clamped at the grid's edges like the taps themselves), (2) the 7-tap blur is evaluated
-// for the tile and 6 bins around it -- at the position its consumer will clamp to, so the
-// nested clamping of the two-kernel recipe is reproduced exactly --, (3) the two-octave blur
-// and the record are written.  Same sums in the same order as k_bilat_prep1 + k_bilat_prep2
-// (which remain as the reference for the equivalence test), 24 instead of 40 bytes of global
-// traffic per bin and one launch less per direction.
-#define PF_T 32
-#define PF_H1 9                         // reach of both blurs together: 3 + 2 * 3
-#define PF_H2 6                         // reach of the two-octave blur
-#define PF_W1 (PF_T + 2 * PF_H1)        // 50: staged densities per row
-#define PF_W2 (PF_T + 2 * PF_H2)        // 44: first-blur values per row
-__global__ void __launch_bounds__(256)
-k_bilat_prep(float2 *side, const float4 *src, int pattern, coefs7 k, float dpow, cb_dims dim) {
-    __shared__ float s_w[PF_W1][PF_W1 + 1];
-    __shared__ float s_a[PF_W2][PF_W2 + 1];
-    const int W = dim.astride, H = dim.aheight;
-    const int x0 = blockIdx.x * PF_T, y0 = blockIdx.y * PF_T;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < PF_W1 * PF_W1; i += 256) {
-        const int ty = i / PF_W1, tx = i - ty * PF_W1;
-        s_w[ty][tx] = src[clamp_idx(x0 - PF_H1 + tx, y0 - PF_H1 + ty, W, H)].w;
-    }
-    int2 o1[7], o2[7];
-#pragma unroll
-    for (int i = 0; i < 7; i++) {
-        o1[i] = shear_offset(pattern, (float)(i - 3));
-        o2[i] = shear_offset(pattern, (float)((i - 3) * 2));
-    }
-    __syncthreads();
-    for (int i = tid; i < PF_W2 * PF_W2; i += 256) {
-        const int ty = i / PF_W2, tx = i - ty * PF_W2;
-        // the consumer reads aux at clamp(p + o2): evaluate the blur there
-        const int qx = min(max(x0 - PF_H2 + tx, 0), W - 1), qy = min(max(y0 - PF_H2 + ty, 0), H - 1);
-        float den = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 7; t++) {
-            const int gx = min(max(qx + o1[t].x, 0), W - 1), gy = min(max(qy + o1[t].y, 0), H - 1);
-            den += s_w[gy - (y0 - PF_H1)][gx - (x0 - PF_H1)] * k.c[t];
-        }
-        s_a[ty][tx] = den;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const int ly = threadIdx.y + 8 * p, lx = threadIdx.x;
-        const int yi = y0 + ly, xi = x0 + lx;
-        if (yi >= H) break;
-        float den = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 7; t++)
-            den += s_a[ly + PF_H2 + o2[t].y][lx + PF_H2 + o2[t].x] * k.c[t];
-        side[yi * W + xi] = make_float2(1.0f / (den + 1.0e-6f),
-                                        powf(s_w[ly + PF_H1][lx + PF_H1], dpow));
-    }
-}
-
 // The same per-pixel record from a two-octave blur plane the caller computed itself
 // (cb_den_blur + cb_den_blur_1c, the reference's launch sequence filters.py:80-92).
 __global__ void __launch_bounds__(256)
@@ -1371,18 +1313,14 @@ int cb_bilateral_direction(cb_dptr dst4, cb_dptr src4, cb_dptr scratch4, int pat
     float2 *side = aux + (size_t)nbins(dim);
     coefs7 k = load_coefs(coefs);
     const dim3 pgrid(dim->astride / 32, (dim->aheight + 8 * PREP_PER - 1) / (8 * PREP_PER));
-    const char *split = getenv("CB_BILAT_PREP_SPLIT");     // tests: the two-kernel prologue
-    if (split && split[0] == '1') {
-        k_bilat_prep1<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(
-            aux, cb_ptr<const float4>(src4), pattern, k, dpow, *dim);
-        CB_LAUNCH_CHECK();
-        k_bilat_prep2<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
-        CB_LAUNCH_CHECK();
-    } else {
-        k_bilat_prep<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(
-            side, cb_ptr<const float4>(src4), pattern, k, dpow, *dim);
-        CB_LAUNCH_CHECK();
-    }
+    // (a fused single-launch prologue through a shared-memory tile was built and measured:
+    // bit-identical, but 31.7 us against 13.8 + 9.9 us -- the halo makes it evaluate the
+    // first blur 1.9 x as often, and it is issue-bound; profiles/r02_filter_kernels.md)
+    k_bilat_prep1<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(
+        aux, cb_ptr<const float4>(src4), pattern, k, dpow, *dim);
+    CB_LAUNCH_CHECK();
+    k_bilat_prep2<<<pgrid, dim3(32, 8), 0, cb_cs(s)>>>(side, aux, pattern, k, *dim);
+    CB_LAUNCH_CHECK();
     return bilateral_main(cb_ptr<float4>(dst4), cb_ptr<const float4>(src4), side, pattern,
                           radius, sstd, cstd, dstd, gspeed, dim, s);
 }

@@ -226,35 +226,6 @@ def test_tile_kernel_equals_the_window_kernel_on_the_transposed_field(native, bu
     assert np.abs(got - want).max() <= 2e-6 * scale, float(np.abs(got - want).max() / scale)
 
 
-@pytest.mark.parametrize('pattern', range(8))
-def test_fused_prologue_equals_the_two_kernel_prologue(native, built, pattern):
-    """k_bilat_prep (both density blurs and the per-pixel record in one launch, staged in
-    shared memory) against k_bilat_prep1 + k_bilat_prep2: the direction pass built on
-    either is identical bit for bit, edges and the ragged last row block included."""
-    import os
-    N = native
-    from cuburn_b200.filters import gauss_coefs
-    dim, f = _field(11 + pattern, 'mixed')
-    src = upload_field(N, f)
-    args = (pattern, 15, gauss_coefs(1), np.float32(6 * W / 1920. * 4), np.float32(0.05),
-            np.float32(1.5), np.float32(0.8), np.float32(4.0))
-    outs = []
-    for split in ('1', None):
-        if split:
-            os.environ['CB_BILAT_PREP_SPLIT'] = split
-        try:
-            scratch, out = N.DeviceBuffer(f.nbytes), N.DeviceBuffer(f.nbytes)
-            N.fill32(scratch, f.nbytes // 4, np.float32(np.nan))
-            N.check(N.lib().cb_bilateral_direction(out.ptr, src.ptr, scratch.ptr, *args,
-                                                   N.byref(dim), None))
-            N.check(N.lib().cb_device_sync())
-            outs.append(N.from_device(out, f.shape, np.float32))
-        finally:
-            os.environ.pop('CB_BILAT_PREP_SPLIT', None)
-    assert np.isfinite(outs[0]).all()
-    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
-
-
 def test_pointwise_tonemap_kernels(native, built):
     N = native
     from oracle import filters_ref as F
