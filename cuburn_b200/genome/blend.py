@@ -227,6 +227,7 @@ def blend(src, dst, edit=None):
     anim = merge_nodes(specs.node, src, dst, edit, duration)
     sxfs, dxfs = src.get('xforms', {}), dst.get('xforms', {})
     anim['xforms'] = {}
+    paired = {}
     for skey, dkey in sort_xforms(sxfs, dxfs, options.xform_sort, explicit=options.xform_map):
         knots = merge_edits(specs.xform, get(edit, {}, 'xforms', 'src', skey),
                             get(edit, {}, 'xforms', 'dst', dkey))
@@ -238,6 +239,8 @@ def blend(src, dst, edit=None):
             knots.setdefault('weight', []).extend([1, 0])
         name = '%s_%s' % (skey or 'pad', dkey or 'pad')
         anim['xforms'][name] = blend_xform(sxfs.get(skey), dxfs.get(dkey), knots, duration)
+        paired[name] = (skey, dkey)
+    _blend_chaos(anim['xforms'], paired, sxfs, dxfs, duration)
     if 'final_xform' in src or 'final_xform' in dst:
         anim['final_xform'] = blend_xform(src.get('final_xform'), dst.get('final_xform'),
                                           edit.get('final_xform'), duration, True)
@@ -247,12 +250,46 @@ def blend(src, dst, edit=None):
 
 
 # ---- xforms --------------------------------------------------------------------------
+def _blend_chaos(blended, pairs, sxfs, dxfs, duration):
+    """
+    Xaos tables (an addition: the reference's blender predates its kernel's xaos support
+    and drops them).  ``chaos[n]`` of an xform multiplies the weight of xform ``n`` when
+    the trajectory comes from this one; in the animation the xforms are the *pairs*, so
+    the entry for pair (s, d) blends the source's entry for ``s`` into the destination's
+    entry for ``d``.  A side that says nothing about a target counts as 1.
+    """
+    spec = specs.xform['chaos'].type
+    for name, (skey, dkey) in pairs.items():
+        sch = (sxfs.get(skey) or {}).get('chaos')
+        dch = (dxfs.get(dkey) or {}).get('chaos')
+        blended[name].pop('chaos', None)            # the schema walk leaves maps to us
+        if sch is None and dch is None:
+            continue
+        table = {}
+        for target, (sk2, dk2) in pairs.items():
+            sv = None if sch is None else sch.get(sk2, sch.get(_as_int(sk2)))
+            dv = None if dch is None else dch.get(dk2, dch.get(_as_int(dk2)))
+            if sv is not None or dv is not None:
+                table[target] = tospline(spec, sv, dv, None, duration)
+        blended[name]['chaos'] = table
+
+
+def _as_int(key):
+    try:
+        return int(key)
+    except (TypeError, ValueError):
+        return None
+
+
 def blend_xform(sxf, dxf, edits, duration, isfinal=False):
     if sxf is None:
         sxf = padding_xform(dxf, isfinal)
     if dxf is None:
         dxf = padding_xform(sxf, isfinal)
-    return merge_nodes(specs.xform, sxf, dxf, edits, duration)
+    out = merge_nodes(specs.xform, sxf, dxf, edits, duration)
+    if out.get('chaos', 0) is None:
+        del out['chaos']                            # maps are blended by the caller
+    return out
 
 
 # Variations with a hole at the origin: shrinking their weight to zero opens the hole

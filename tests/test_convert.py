@@ -216,3 +216,32 @@ def test_reference_generated_golden_vectors():
         got = blend.blend(fresh(gold['nodes'][c['src']]), fresh(gold['nodes'][c['dst']]),
                           fresh(c['edge']))
         assert canon(got) == c['anim'], (c['src'], c['dst'], c['edge'])
+
+
+def test_flam3_chaos_and_opacity_reach_the_iterate_module(built):
+    """A flam3 file with per-xform `chaos` and `opacity` attributes: the converter keeps
+    them (convert.py:180-183), the packer turns them into xaos density slots and an opacity
+    slot, and the generated module (choice chain per previous xform, visibility draw)
+    compiles for sm_100a."""
+    from cuburn_b200 import _native as N
+    from cuburn_b200.code import itergen
+    xforms = ('<xform weight="0.5" color="0" linear="1" coefs="0.5 0 0 0.5 0.3 0" '
+              'chaos="1 0.25" opacity="0.5"/>'
+              '<xform weight="0.5" color="1" spherical="0.4" linear="0.6" coefs="0.6 0 0 0.6 -0.3 0.1" '
+              'chaos="2 1"/>')
+    flame = convert.XMLGenomeParser.parse(_make_genome_src(xforms=xforms))[0]
+    node = convert.flam3_to_node(flame)
+    assert node['xforms']['0']['chaos'] == {'0': 1.0, '1': 0.25}
+    assert node['xforms']['0']['opacity'] == 0.5
+    anim = blend.node_to_anim(None, node, half=False)
+    # the blender carries the tables over, keyed by the blended xform names
+    assert anim['xforms']['0_0']['chaos'] == {'0_0': 1.0, '1_1': 0.25}
+    assert anim['xforms']['1_1']['chaos'] == {'0_0': 2.0, '1_1': 1.0}
+    pk, src = itergen.mkiterlib(anim)
+    assert pk.xaos and len(pk.opacity) == 1
+    for p in pk.xform_ids:
+        for n in pk.xform_ids[:-1]:
+            pk.slot('xforms', p, 'chaos_den', n)
+    assert 'switch (pt.last[0])' in src and 'opacity_visible' in src
+    names, hdrs = itergen.load_headers()
+    assert N.Module(src, 'xaos.cu', hdrs, names, itergen.NVRTC_OPTIONS).cubin[:4] == b'\x7fELF'
