@@ -61,7 +61,8 @@ class IterArgs(ctypes.Structure):
                 ('first_sample', c_uint64), ('nsamples', c_uint64),
                 ('total_samples', c_uint64), ('cells', c_uint64),
                 ('palette_packed', c_uint64), ('hot_tags', c_uint64),
-                ('first_round', c_int32)]
+                ('first_round', c_int32), ('spill', c_uint64), ('spill_bins', c_int32),
+                ('spill_count', c_float), ('tickets', c_uint64), ('dynamic', c_int32)]
 
 
 _SIGNATURES = {
@@ -115,7 +116,9 @@ _SIGNATURES = {
     'cb_palette_pack': (c_int, [c_uint64, c_uint64, c_int, c_void_p]),
     'cb_flush_packed': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_hist_unswizzle': (c_int, [c_uint64, c_uint64, c_int, POINTER(Dims), c_void_p]),
-    'cb_hot_scan': (c_int, [c_uint64, c_uint64, c_uint64, c_uint64, c_int, c_float, c_float,
+    'cb_hist_finish': (c_int, [c_uint64, c_uint64, c_uint64, c_int, c_float,
+                               POINTER(Dims), c_void_p]),
+    'cb_hot_scan': (c_int, [c_uint64, c_uint64, c_uint64, c_uint64, c_uint64, c_int, c_float, c_float,
                             POINTER(Dims), c_void_p]),
     'cb_yuv_to_rgb': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_den_blur': (c_int, [c_uint64, c_uint64, c_int, c_int, POINTER(c_float),

@@ -53,6 +53,16 @@ __device__ __forceinline__ int clamp_idx(int x, int y, int w, int h) {
     int yi = blockIdx.y * 8 + threadIdx.y;                        \
     int gi = yi * dim.astride + xi
 
+// Inverse of the slice-balancing accumulation layout (device/iter_kernel.cuh).
+struct op_unswizzle_index {
+    int swizzle_bins;
+    __device__ __forceinline__ int index(int i) const {
+        unsigned int u = (unsigned int)i;
+        unsigned int j = (u & 0xffff0000u) | ((u * 40503u) & 0xffffu);
+        return i < swizzle_bins ? (int)j : i;
+    }
+};
+
 // ---- pointwise kernels -------------------------------------------------------------
 // Each filter is a small functor; the three kernel templates below apply it to
 // PW_PER x 256 consecutive bins per CTA, with every thread issuing all of its
@@ -75,6 +85,36 @@ k_map4(float4 *dst, const float4 *src, int n, Op op) {
     for (int k = 0; k < PW_PER; k++) {
         int i = base + k * 256;
         if (i < n) dst[i] = op(v[k]);
+    }
+}
+
+// End of the float4 accumulation (device/iter_kernel.cuh): the histogram holds integer
+// level sums in the accumulation layout, full bins were moved to a second grid in the same
+// layout; the filters want (sum Y / 255, sum U / 255, sum V / 255, count) in linear layout
+// (iter.py:395-406).
+__global__ void __launch_bounds__(256)
+k_hist_finish(float4 *dst, const float4 *hist, const float4 *spill, int n, int swizzle_bins,
+              float k) {
+    op_unswizzle_index ix;
+    ix.swizzle_bins = swizzle_bins;
+    const int base = blockIdx.x * (256 * PW_PER) + threadIdx.x;
+    float4 v[PW_PER], w[PW_PER];
+#pragma unroll
+    for (int q = 0; q < PW_PER; q++) {
+        int i = base + q * 256;
+        w[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (i < n) {
+            const int j = ix.index(i);
+            v[q] = hist[j];
+            if (spill) w[q] = spill[j];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PW_PER; q++) {
+        int i = base + q * 256;
+        if (i < n)
+            dst[i] = make_float4((v[q].x + w[q].x) * k, (v[q].y + w[q].y) * k,
+                                 (v[q].z + w[q].z) * k, v[q].w + w[q].w);
     }
 }
 
@@ -144,14 +184,7 @@ __device__ __forceinline__ float4 scaled(float4 p, float s) {
     return make_float4(p.x * s, p.y * s, p.z * s, p.w * s);
 }
 
-// Inverse of the slice-balancing accumulation layout (device/iter_kernel.cuh).
-struct op_unswizzle {
-    int swizzle_bins;
-    __device__ __forceinline__ int index(int i) const {
-        unsigned int u = (unsigned int)i;
-        unsigned int j = (u & 0xffff0000u) | ((u * 40503u) & 0xffffu);
-        return i < swizzle_bins ? (int)j : i;
-    }
+struct op_unswizzle : op_unswizzle_index {
     __device__ __forceinline__ float4 operator()(float4 p) const { return p; }
 };
 
@@ -291,11 +324,11 @@ __constant__ unsigned int c_hot_muls[HOT_TRIES] = {
     374761393u, 1540483477u, 2891336453u, 4182319919u};
 
 __global__ void __launch_bounds__(256)
-k_hot_scan(unsigned long long *best, int *ntrigger, const float4 *hist, int nbins,
-           int swizzle_bins, float threshold, float trigger) {
+k_hot_scan(unsigned long long *best, int *ntrigger, const float4 *hist, const float4 *spill,
+           int nbins, int swizzle_bins, float threshold, float trigger) {
     const int i = blockIdx.x * 256 + threadIdx.x;      // storage index
     if (i >= nbins) return;
-    const float w = hist[i].w;
+    const float w = hist[i].w + (spill ? spill[i].w : 0.0f);
     if (w < threshold) return;
     unsigned int u = (unsigned int)i;
     if (i < swizzle_bins) u = (u & 0xffff0000u) | ((u * HIST_SWZ_INV) & 0xffffu);
@@ -1085,7 +1118,7 @@ int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream 
     return CB_OK;
 }
 
-int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
+int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4, cb_dptr spill4,
                 int swizzle_bins, float threshold, float trigger, const cb_dims *dim,
                 cb_stream s) {
     CHECK_DIM(dim);
@@ -1094,7 +1127,7 @@ int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
     CB_REQUIRE(threshold >= 1.0f && trigger >= threshold, "need 1 <= threshold <= trigger");
     k_hot_scan<<<(nbins(dim) + 255) / 256, 256, 0, cb_cs(s)>>>(
         cb_ptr<unsigned long long>(scratch), cb_ptr<int>(count) + 1, cb_ptr<const float4>(hist4),
-        nbins(dim), swizzle_bins, threshold, trigger);
+        cb_ptr<const float4>(spill4), nbins(dim), swizzle_bins, threshold, trigger);
     CB_LAUNCH_CHECK();
     k_hot_finish<<<1, HOT_SLOTS, 0, cb_cs(s)>>>(cb_ptr<int>(tags), cb_ptr<int>(count),
                                                 cb_ptr<unsigned long long>(scratch));
@@ -1109,6 +1142,19 @@ int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins, const cb_dim
     op_unswizzle op;
     op.swizzle_bins = swizzle_bins;
     MAP4(dst4, src4, op);
+}
+
+int cb_hist_finish(cb_dptr dst4, cb_dptr hist4, cb_dptr spill4, int swizzle_bins,
+                   float level_scale, const cb_dims *dim, cb_stream s) {
+    CHECK_DIM(dim);
+    CB_REQUIRE(swizzle_bins >= 0 && swizzle_bins % 65536 == 0 && swizzle_bins <= nbins(dim),
+               "swizzle_bins must be a multiple of 65536 inside the grid");
+    CB_REQUIRE(swizzle_bins == 0 || dst4 != hist4, "in place only for the linear layout");
+    k_hist_finish<<<pw_grid(dim), 256, 0, cb_cs(s)>>>(
+        cb_ptr<float4>(dst4), cb_ptr<const float4>(hist4), cb_ptr<const float4>(spill4),
+        nbins(dim), swizzle_bins, level_scale);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s) {

@@ -229,7 +229,11 @@ int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas, cb_stream s
     CB_REQUIRE(grid_ctas > 0, "grid_ctas must be positive");
     CB_REQUIRE(args->first_sample % 16384ull == 0, "first_sample must be unit aligned");
     CB_REQUIRE(args->nts > 0 && args->pal_rows > 0, "bad temporal sample counts");
+    CB_REQUIRE(args->tickets || (!args->dynamic && !args->spill),
+               "tickets scratch needed for dynamic units and for the spill sweep");
     cb_iter_args a = *args;
+    if (a.tickets)
+        CB_CUDA(cudaMemsetAsync((void *)a.tickets, 0, 8, cb_cs(s)));
     void *kargs[1] = {&a};
     return cb_module_launch(m, "cb_iter", grid_ctas, 1, 1, 256, 1, 1, 0, kargs, s);
 }

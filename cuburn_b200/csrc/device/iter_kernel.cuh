@@ -37,9 +37,10 @@
 //     launch renders a whole frame and every RNG stream / trajectory belongs to
 //     one thread for the frame (no ring buffer, no block-slot atomics)
 //   * accumulation is a single 16-byte red.global.add.v4.f32 per sample straight
-//     into the float4 histogram, which is L2-resident on B200 up to 1080p+;
-//     the packed-u64 cells, the overflow spill and the flush kernel of the
-//     reference (iter.py:332-407, 420-544) disappear, as does hotspot thinning
+//     into the float4 histogram, which is L2-resident on B200 up to 1080p+: integer
+//     palette levels and a count, kept exact by a sweep that moves full bins aside
+//     (spill_sweep below) instead of the reference's per-sample overflow check
+//     (iter.py:359-407); hotspot thinning is replaced by HOT_BINS
 //   * the point exchange is double-buffered so a round costs one barrier, and
 //     the unit's palette row is staged in shared memory so the per-sample colour
 //     fetch is an LDS.128 instead of a scattered global load
@@ -66,6 +67,11 @@ struct iter_args {
     const unsigned long long *palette_packed;  // u64 [pal_rows][256] (ACC_PACKED, PAL_COMPACT)
     const int *hot_tags;                       // HOT_BINS: int [HOT_SLOTS + 1]: bin or -1, then the hash multiplier
     int first_round;        // phase of the exchange permutation to start from
+    float4 *spill;          // float4 path: where swept bins are moved to (layout of hist), or 0
+    int spill_bins;         // bins of hist every unit examines
+    float spill_count;      // a bin holding at least this many samples is moved
+    unsigned int *tickets;  // [0]: next unit to hand out (dynamic), [1]: sweep windows begun
+    int dynamic;            // 0: CTA b runs units b, b + grid, ...; 1: units are claimed
 };
 
 #ifndef ACC_PACKED
@@ -114,6 +120,86 @@ struct iter_args {
 __device__ __forceinline__ void red_add_f32x4(float4 *addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- exact sums in a float4 histogram -------------------------------------------------
+// The float4 path adds *integer-valued* floats: 8-bit palette levels and a count of 1 (the
+// reference's addends, interp.py:428-429, iter.py:334-351; the division by 255 of
+// iter.py:395-406 happens once per bin in cb_hist_finish).  Such a sum is exact while it
+// stays below 2^24, i.e. for 65793 samples of the brightest level, and a float add has no
+// way of telling that it is about to round.  So the grid is *swept*: every unit looks at
+// spill_bins bins (a window that advances with the unit index and wraps around the grid)
+// and moves the ones holding >= spill_count samples -- one 128-bit exchange with zero and
+// one reduction into the `spill` grid, which receives a bin's sum in chunks of < 2^24 and
+// therefore rounds each chunk by at most 2^-24 of the total.  Windows are numbered by a
+// ticket counter in the order in which units *begin* (CTAs run at different speeds, the
+// unit index is not a clock), and the host sizes them so that the grid is swept once per
+// ~2^26 samples of the launch: a bin would have to collect more than 65793 - spill_count
+// samples between two sweeps to lose a bit (1/1088 of all samples; bins much hotter than
+// that are what HOT_BINS is for).  The reference spills its 10-bit counters at 512 the same
+// way (iter.py:359-407), driven by the value its atom.add returns; a sweep costs a
+// 4-byte copy per bin and sweep instead of an atomic round trip per sample.
+__device__ __forceinline__ float4 exch_zero_f32x4(float4 *addr) {
+    unsigned long long lo, hi;
+    asm volatile("{\n\t.reg .b128 z, o;\n\tmov.b128 z, {%3, %3};\n\t"
+                 "atom.global.exch.b128 o, [%2], z;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(lo), "=l"(hi) : "l"(addr), "l"(0ull) : "memory");
+    return make_float4(__uint_as_float((unsigned int)lo), __uint_as_float((unsigned int)(lo >> 32)),
+                       __uint_as_float((unsigned int)hi), __uint_as_float((unsigned int)(hi >> 32)));
+}
+
+// Split in two so that nobody waits for the counts: at the start of a unit every thread
+// asks for the counts of its bins of the window with 4-byte asynchronous copies into
+// shared memory (LDGSTS: no register, no scoreboard), at the end of the unit -- 64 rounds
+// later -- it looks at them.  A count read a unit ago only errs on the low side.
+#define SWEEP_MAX_WINDOW (2 * ITER_THREADS)
+
+__device__ __forceinline__ int sweep_bin(int base, int i, int nbins) {
+    const int b = base + i;
+    return b >= nbins ? b - nbins : b;
+}
+
+#ifndef SWEEP_HINT
+#define SWEEP_HINT 0
+#endif
+__device__ __forceinline__ void sweep_begin(float *counts, const float4 *hist, int nbins, int base,
+                                            int window, int tid) {
+#if SWEEP_HINT
+    unsigned long long pol;
+#if SWEEP_HINT == 1
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+#endif
+#endif
+#pragma unroll
+    for (int k = 0; k < SWEEP_MAX_WINDOW / ITER_THREADS; k++) {
+        const int i = tid + k * ITER_THREADS;
+        if (i < window)
+#if SWEEP_HINT
+            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;"
+                         :: "r"((unsigned int)__cvta_generic_to_shared(counts + i)),
+                            "l"(&hist[sweep_bin(base, i, nbins)].w), "l"(pol) : "memory");
+#else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                         :: "r"((unsigned int)__cvta_generic_to_shared(counts + i)),
+                            "l"(&hist[sweep_bin(base, i, nbins)].w) : "memory");
+#endif
+    }
+}
+
+__device__ __forceinline__ void sweep_end(const float *counts, float4 *hist, float4 *spill,
+                                          int nbins, int base, int window, float count, int tid) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < SWEEP_MAX_WINDOW / ITER_THREADS; k++) {
+        const int i = tid + k * ITER_THREADS;
+        if (i < window && counts[i] >= count) {
+            const int b = sweep_bin(base, i, nbins);
+            const float4 v = exch_zero_f32x4(hist + b);
+            red_add_f32x4(spill + b, v);
+        }
+    }
 }
 
 // ---- packed accumulation (grids far larger than L2) ---------------------------------
@@ -240,10 +326,9 @@ __device__ __forceinline__ void hot_flush(hot_table *ht, const iter_args &a, int
     for (int s = tid; s < HOT_SLOTS; s += ITER_THREADS) {
         const unsigned int n = ht->cell[s][0];
         if (n) {
-            const float k = 1.0f / 255.0f;
             red_add_f32x4(a.hist + swizzle_bin(ht->tag[s], a.swizzle_bins),
-                          make_float4((float)ht->cell[s][1] * k, (float)ht->cell[s][2] * k,
-                                      (float)ht->cell[s][3] * k, (float)n));
+                          make_float4((float)ht->cell[s][1], (float)ht->cell[s][2],
+                                      (float)ht->cell[s][3], (float)n));
             ht->cell[s][0] = 0u; ht->cell[s][1] = 0u; ht->cell[s][2] = 0u; ht->cell[s][3] = 0u;
         }
     }
@@ -334,6 +419,10 @@ struct iter_smem {
     hot_table hot;
     unsigned int hot_mul;
 #endif
+    unsigned int claim[2];              // unit and sweep window of the CTA's current unit
+#if !ACC_PACKED
+    float sweep_counts[SWEEP_MAX_WINDOW];   // counts of the window's bins (spill sweep)
+#endif
 };
 
 __device__ __forceinline__ unsigned int compact_levels(unsigned long long packed) {
@@ -358,10 +447,9 @@ __device__ __forceinline__ void record_sample(const iter_args &a, iter_smem &sm,
         return;
     }
 #endif
-    const float k = 1.0f / 255.0f;
     red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins),
-                  make_float4(__uint2float_rn(lv >> 16) * k, __uint2float_rn((lv >> 8) & 0xffu) * k,
-                              __uint2float_rn(lv & 0xffu) * k, 1.0f));
+                  make_float4(__uint2float_rn(lv >> 16), __uint2float_rn((lv >> 8) & 0xffu),
+                              __uint2float_rn(lv & 0xffu), 1.0f));
 #else
     red_add_f32x4(a.hist + swizzle_bin(bin, a.swizzle_bins), sm.pal[cidx]);
 #endif
@@ -384,6 +472,15 @@ cb_iter(const __grid_constant__ iter_args a) {
 
     mwc_st rng = a.seeds[gtid];
     point_set pt;
+#ifdef SPILL_DEBUG
+    if (tid == 0 && a.hot_tags) {
+        unsigned long long t; unsigned int smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        unsigned long long *tt = (unsigned long long *)(a.hot_tags + 1024);
+        tt[blockIdx.x * 3] = t; tt[blockIdx.x * 3 + 2] = smid;
+    }
+#endif
 
     const unsigned long long unit0 = a.first_sample / UNIT_SAMPLES;
     const unsigned long long nunits = (a.nsamples + UNIT_SAMPLES - 1) / UNIT_SAMPLES;
@@ -412,12 +509,30 @@ cb_iter(const __grid_constant__ iter_args a) {
     int units_done = 0;
 #endif
 
-    for (unsigned long long lu = blockIdx.x; lu < nunits || fresh; lu += gridDim.x) {
+    // Which CTA runs which unit.  The CTAs of a persistent grid do not run at one speed:
+    // the warp schedulers favour the warps that were launched first, and on an issue-bound
+    // kernel the first CTA of an SM runs twice as fast as the last (measured: with units
+    // dealt out statically the first CTAs are done after 48 % of the launch and the tail
+    // runs on a quarter of the warps, tools/cta_timeline.py).  dynamic = 1: a CTA claims
+    // its next unit from a counter when it is ready for it, so that all finish within a
+    // unit of each other; which stream draws which unit then depends on timing.
+    // dynamic = 0: unit lu belongs to CTA lu mod grid -- the sample set is a pure function
+    // of the seeds (parity tests, reproducible frames).
+    unsigned long long lu = blockIdx.x;
+    for (;; lu += gridDim.x) {
+        if (tid == 0) {
+            if (a.dynamic) sm.claim[0] = atomicAdd(&a.tickets[0], 1u);
+#if !ACC_PACKED
+            if (a.spill) sm.claim[1] = atomicAdd(&a.tickets[1], 1u);
+#endif
+        }
+        __syncthreads();            // everyone is done with the previous unit's tables
+        if (a.dynamic) lu = sm.claim[0];
+        if (!(lu < nunits || fresh)) break;
         // temporal sample of this unit: contiguous runs of units per sample
         unsigned long long u = unit0 + (lu < nunits ? lu : 0);
         int ts = (int)((u * (unsigned long long)a.nts) / frame_units);
         int row = ts * a.pal_rows / a.nts;
-        __syncthreads();            // everyone is done with the previous unit's tables
 #if !PARAMS_CONST
         for (int i = tid; i < NSLOTS; i += ITER_THREADS)
             s_params[i] = a.params[(size_t)ts * a.param_stride + i];
@@ -428,13 +543,28 @@ cb_iter(const __grid_constant__ iter_args a) {
 #elif PAL_COMPACT
             sm.palc[tid] = compact_levels(a.palette_packed[row * 256 + tid]);
 #else
-            sm.pal[tid] = a.palette[row * 256 + tid];
+            {
+                // level / 255 (cb_interp_palette) back to the level itself: exact
+                const float4 q = a.palette[row * 256 + tid];
+                sm.pal[tid] = make_float4(rintf(q.x * 255.0f), rintf(q.y * 255.0f),
+                                          rintf(q.z * 255.0f), q.w);
+            }
 #endif
             cur_row = row;
         }
 #if HOT_BINS
         if (units_done && units_done % HOT_FLUSH_UNITS == 0) hot_flush(&sm.hot, a, tid);
         units_done++;
+#endif
+#if !ACC_PACKED
+        const int nbins = a.dim.aheight * a.dim.astride;
+        const bool sweeping = a.spill && lu < nunits;
+        int sweep_base = 0;
+        if (sweeping) {
+            sweep_base = (int)(((unsigned long long)sm.claim[1] * (unsigned long long)a.spill_bins)
+                               % (unsigned long long)nbins);
+            sweep_begin(sm.sweep_counts, a.hist, nbins, sweep_base, a.spill_bins, tid);
+        }
 #endif
         __syncthreads();
 
@@ -491,6 +621,11 @@ cb_iter(const __grid_constant__ iter_args a) {
                 if (bin[p] >= 0) record_sample(a, sm, bin[p], cidx[p], word, lane);
 #endif
         }
+#if !ACC_PACKED
+        if (sweeping)
+            sweep_end(sm.sweep_counts, a.hist, a.spill, nbins, sweep_base, a.spill_bins,
+                      a.spill_count, tid);
+#endif
     }
 #if HOT_BINS
     __syncthreads();
@@ -501,6 +636,13 @@ cb_iter(const __grid_constant__ iter_args a) {
     for (int p = 0; p < POINTS; p++)
         a.points[p * POINT_STRIDE + gtid] = make_float4(pt.x[p], pt.y[p], pt.c[p], 0.0f);
     a.seeds[gtid] = rng;
+#ifdef SPILL_DEBUG
+    if (tid == 0 && a.hot_tags) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        ((unsigned long long *)(a.hot_tags + 1024))[blockIdx.x * 3 + 1] = t;
+    }
+#endif
 }
 
 #if !PARAMS_CONST

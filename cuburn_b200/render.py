@@ -299,6 +299,7 @@ class RenderManager(object):
         self._hot_probe = None          # (event, pinned count, renderer) of the last scan
         self._hot_counts = self.fb.pool.allocate((8,), 'i4')       # pinned ring of results
         self._hot_seq = 0
+        self.d_tickets = N.DeviceBuffer(16)     # unit / sweep counters of a cb_iterate launch
         # share of the frame's samples this manager renders (multi-GPU stills)
         self.sample_share = (rank, world)
         self.hist_hook = None
@@ -411,9 +412,42 @@ class RenderManager(object):
     hot_pilot = 64
     hot_min_waves = 4               # frames shorter than this many waves of units: never
 
+    # Exact sums on the float4 path (device/iter_kernel.cuh, spill_sweep): the kernel adds
+    # integer palette levels, and sweeps the grid once per ``spill_interval`` samples,
+    # moving every bin that holds >= ``spill_count`` samples into a second grid.  A sum
+    # stays exact while it is below 2^24 = 65793 samples of level 255, so a bin would have
+    # to collect 65793 - spill_count samples between two sweeps (1/1088 of all samples at
+    # the defaults) before a float add rounds; much hotter bins are what ``hot_bins`` is for.
+    # Grids that do not stay L2-resident are swept less often -- a sweep pulls every sector of
+    # the grid through L2, the untouched background included, and costs ~0.5 % of a 4K /
+    # 500 spp launch (measured, profiles/r02_schedule_and_sweep.md) -- so there the bound on
+    # a bin's rounding error only improves by the number of sweeps.  False: no sweeps (sums
+    # round like any float32 running sum, relative error up to n * 2^-25 for a bin of n
+    # samples).
+    spill = True
+    spill_interval = 1 << 26
+    spill_count = 4096.0
+    spill_max_window = 512          # SWEEP_MAX_WINDOW of device/iter_kernel.cuh
+
+    def _spill_window(self, nbins, n):
+        """Bins every unit examines, for a launch of n samples."""
+        if not self.spill or n <= 0:
+            return 0
+        nunits = (n + UNIT_SAMPLES - 1) // UNIT_SAMPLES
+        sweeps = max(1, -(-n // self.spill_interval))
+        if not hasattr(self, '_l2_bytes'):
+            self._l2_bytes = N.device_info(N._initialised or 0)['l2_bytes']
+        if 16 * nbins > 0.6 * self._l2_bytes:
+            sweeps = min(sweeps, max(1, int(0.005 * n / nbins)))
+        return int(min(-(-nbins * sweeps // nunits), self.spill_max_window, nbins))
+
     def _launch_iter(self, mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
                      hot, s, first_round=0):
+        window = 0 if packed else self._spill_window(dim.ah * dim.astride, n)
         args = N.IterArgs(
+            spill=self.fb.d_right.ptr if window else 0, spill_bins=window,
+            spill_count=self.spill_count, tickets=self.d_tickets.ptr,
+            dynamic=int(self.schedule == 'dynamic'),
             hist=int(d_acc), swizzle_bins=swz, seeds=self.fb.d_seeds.ptr,
             points=self.fb.d_points.ptr, params=info.d_params.ptr,
             palette=info.d_palette.ptr, dim=dim, param_stride=rdr.packer.param_stride,
@@ -428,6 +462,14 @@ class RenderManager(object):
 
     # persistent CTAs per cb_iterate launch; None: fill the GPU at the module's occupancy
     iter_grid = None
+
+    # How units of 16384 samples are dealt out to the persistent CTAs.  'dynamic': a CTA
+    # claims its next unit when it is ready for it -- the CTAs of an SM run at very
+    # different speeds (the warp schedulers favour the oldest warps), and with static
+    # ownership the slow ones finish the launch alone.  'static': CTA b runs units
+    # b, b + grid, ...: every RNG stream draws the same samples in every run, so a frame
+    # is a pure function of its seeds (reproducible frames; what the parity tests use).
+    schedule = 'dynamic'
 
     def _hot_decision(self, rdr, nunits, packed, grid):
         """(run the pilot + scan?, use the HOT_BINS variant?) for this frame."""
@@ -449,7 +491,13 @@ class RenderManager(object):
         nbins = dim.ah * dim.astride
         packed = self._use_packed(nbins)
         swz = (nbins // 65536) * 65536 if (not packed and self._use_swizzle(nbins)) else 0
-        d_acc = self.fb.d_left if swz else self.fb.d_front
+        # float4 path: integer level sums in d_left (+ swept bins in d_right), scaled and
+        # brought into linear layout in d_front by cb_hist_finish; packed path: u64 cells
+        # in d_left, drained into d_front
+        d_acc = self.fb.d_front if packed else self.fb.d_left
+        if not packed and self.spill:
+            N.fill32(self.fb.d_right, 4 * nbins, 0, s)
+        # the grid the samples go to is cleared last: what of it fits stays in L2
         N.fill32(d_acc, 4 * nbins, 0, s)
         if packed:
             N.fill32(self.fb.d_left, 2 * nbins, 0, s)           # u64 cells
@@ -473,7 +521,8 @@ class RenderManager(object):
                               packed, False, s)
             N.check(N.lib().cb_hot_scan(
                 self.d_hot.ptr + HOT_TAGS_OFF, self.d_hot.ptr + HOT_COUNT_OFF, self.d_hot.ptr,
-                int(d_acc), swz, np.float32(max(32.0, self.hot_share * npilot)),
+                int(d_acc), self.fb.d_right.ptr if self.spill else 0, swz,
+                np.float32(max(32.0, self.hot_share * npilot)),
                 np.float32(max(32.0, self.hot_trigger * npilot)), N.byref(dim), s.handle))
             self._hot_seq = (self._hot_seq + 1) % 8
             probe = self._hot_counts[self._hot_seq:self._hot_seq + 1]
@@ -503,9 +552,10 @@ class RenderManager(object):
         if packed:
             N.check(N.lib().cb_flush_packed(self.fb.d_front.ptr, self.fb.d_left.ptr,
                                             N.byref(dim), s.handle))
-        if swz:
-            N.check(N.lib().cb_hist_unswizzle(int(self.fb.d_front), int(d_acc), swz,
-                                              N.byref(dim), s.handle))
+        else:
+            N.check(N.lib().cb_hist_finish(
+                self.fb.d_front.ptr, int(d_acc), self.fb.d_right.ptr if self.spill else 0, swz,
+                np.float32(1.0 / 255.0), N.byref(dim), s.handle))
         self.last_iter_samples = n_frame
         self.last_iter_hot = bool(hot)
 

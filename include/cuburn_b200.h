@@ -148,7 +148,10 @@ int cb_module_set_global(cb_module m, const char *symbol, cb_dptr src,
                          size_t bytes, cb_stream s);
 
 typedef struct {
-    cb_dptr hist;        /* float4 [aheight][astride] accumulation buffer */
+    cb_dptr hist;        /* float4 [aheight][astride] accumulation buffer.  The float4
+                            modules add integer palette levels (sum Y, sum U, sum V of
+                            8-bit levels, count): cb_hist_finish scales them to the
+                            (sum/255, count) the filters consume */
     cb_dptr seeds;       /* mwc_st [nstreams] */
     cb_dptr points;      /* float4 [nstreams] trajectory state (x, y, color, -) */
     cb_dptr params;      /* float [nts][param_stride] from cb_interp_params */
@@ -173,6 +176,18 @@ typedef struct {
     int32_t first_round;     /* rounds every CTA has run in earlier calls of this frame
                                 (fuse rounds included): a frame split over several calls
                                 then draws the same samples as one call would */
+    cb_dptr spill;           /* float4 modules: 0, or a zeroed float4 grid (layout of hist)
+                                that receives the bins the in-kernel sweep finds full, so
+                                that the float sums in hist stay below 2^24 and exact
+                                (the reference's spill, iter.py:359-407, done by sweeping) */
+    int32_t spill_bins;      /* bins every unit of 16384 samples examines */
+    float spill_count;       /* a bin holding >= this many samples is moved to spill */
+    cb_dptr tickets;         /* uint32 [2] scratch, zeroed by cb_iterate: unit and sweep counters */
+    int32_t dynamic;         /* 0: CTA b runs units b, b + grid_ctas, ... (the sample set is a
+                                pure function of the seeds); 1: CTAs claim units from a
+                                counter as they become ready (balances the 2x spread in CTA
+                                speed of a persistent grid; which stream draws which unit
+                                then depends on timing) */
 } cb_iter_args;
 /* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
  * accumulated into hist.  grid_ctas persistent CTAs of 256 threads; work is
@@ -198,16 +213,23 @@ int cb_flush_packed(cb_dptr hist4, cb_dptr cells, const cb_dims *dim, cb_stream 
  * [4] (zeroed once): count[0] receives the number of bins holding >= trigger samples,
  * count[2] the number of table entries.  `scratch` = 8 x 1024 zeroed u64 (left zeroed).
  * The HOT_BINS variant of the iterate module accumulates the listed bins in shared
- * memory as integer level sums and folds them into the histogram itself. */
+ * memory as integer level sums and folds them into the histogram itself.  `spill4`: 0 or
+ * the spill grid of the pilot pass (a bin's count is the sum of both). */
 int cb_hot_scan(cb_dptr tags, cb_dptr count, cb_dptr scratch, cb_dptr hist4,
-                int swizzle_bins, float threshold, float trigger, const cb_dims *dim,
-                cb_stream s);
+                cb_dptr spill4, int swizzle_bins, float threshold, float trigger,
+                const cb_dims *dim, cb_stream s);
 
 /* Undo the accumulation layout: dst[i] = src[swizzle(i)] for i < swizzle_bins,
  * dst[i] = src[i] above; dst is the linear float4 [aheight][astride] histogram the
  * filters consume (iter.py:395-406 semantics). */
 int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins,
                       const cb_dims *dim, cb_stream s);
+/* End of the float4 accumulation: dst[i] = (hist[j] + spill[j]) * (k, k, k, 1) with
+ * j = swizzle(i) as above and k = level_scale (1/255: level sums -> the (sum Y/255,
+ * sum U/255, sum V/255, count) of iter.py:395-406).  spill4 may be 0; dst4 may equal
+ * hist4 only when swizzle_bins == 0. */
+int cb_hist_finish(cb_dptr dst4, cb_dptr hist4, cb_dptr spill4, int swizzle_bins,
+                   float level_scale, const cb_dims *dim, cb_stream s);
 
 /* ---- filters (code/filters.py; host recipes in cuburn/filters.py) -------- */
 int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s);

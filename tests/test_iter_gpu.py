@@ -263,6 +263,7 @@ def test_density_parity(native, built, gname, w, h, spp):
     ('G24H', 7680, 4320, 25, 'auto'),          # config 5: the packed-u64 path ('auto' there)
     ('G6F', 1920, 1080, 200, 'packed'),        # the packed path on an L2-resident grid
 ])
+@pytest.mark.production_schedule
 def test_density_parity_at_benchmark_sizes(native, built, gname, w, h, spp, accumulate):
     """The accumulated histogram against the oracle at the resolutions bench.py runs
     (oracle: 3-10 s per histogram on the box's cores): GPU-vs-oracle z spread within 10 %
@@ -382,12 +383,17 @@ def test_hot_scan_finds_the_hot_bins(native, built):
         store[low] = (store[low] & ~0xffff) | ((store[low] * 40503) & 0xffff)
         heat = 1000 + np.arange(300)
         hist[store, 3] = heat
-        d_h = N.to_device(hist)
+        # part of some bins' samples sits in the spill grid of the sweep (same layout)
+        moved = np.zeros_like(hist)
+        part = store[::3]
+        moved[part, 3] = np.floor(hist[part, 3] * 0.75)
+        hist[part, 3] -= moved[part, 3]
+        d_h, d_sp = N.to_device(hist), N.to_device(moved)
         d_tab = N.DeviceBuffer(HOT_BYTES)
         N.fill32(d_tab, HOT_BYTES // 4, 0)
         for rep in range(2):                                # the second run reuses the scratch
             N.check(N.lib().cb_hot_scan(d_tab.ptr + HOT_TAGS_OFF, d_tab.ptr + HOT_COUNT_OFF,
-                                        d_tab.ptr, d_h.ptr, swz, np.float32(100.0),
+                                        d_tab.ptr, d_h.ptr, d_sp.ptr, swz, np.float32(100.0),
                                         np.float32(1200.0), N.byref(dim), None))
         N.check(N.lib().cb_device_sync())
         tab = N.from_device(d_tab, (HOT_BYTES,), np.uint8)
@@ -436,6 +442,39 @@ def test_hot_bins_are_exact_and_found_automatically(native, built):
     assert i4['hot'] is False
 
 
+@pytest.mark.production_schedule
+def test_dynamic_schedule_draws_every_unit_once(native, built):
+    """The shipped schedule hands units to CTAs on demand (which stream draws which unit
+    depends on timing): the number of recorded samples is still exact, run after run.
+    (That the samples follow the right measure is test_density_parity_at_benchmark_sizes,
+    which runs under this schedule.)"""
+    N = native
+    from cuburn_b200 import samples, render
+    gnm = samples.g3()
+    gnm['camera']['scale'] = 0.05         # everything lands inside the frame
+    w, h, spp = 640, 360, 300
+    gprof, tc = still_profile(gnm, w, h, spp)
+    ts, td = frame_window(gprof, tc)
+    rmgr = render.RenderManager(seed=4)
+    assert rmgr.schedule == 'dynamic'
+    rdr = render.Renderer(gnm, gprof)
+    dim = rmgr.fb.set_dim(w, h)
+    rmgr._copy(rdr, gnm)
+    rmgr._interp(rdr, gnm, dim, ts, td)
+    hists = []
+    for rep in range(3):
+        rmgr.fb.reseed(4)
+        rmgr._iter(rdr, gnm, gprof, dim, tc)
+        rmgr.stream_a.synchronize()
+        hists.append(N.from_device(rmgr.fb.d_front, (dim.ah, dim.astride, 4), np.float32))
+    n = w * h * spp
+    for hist in hists:
+        got = float(hist[..., 3].astype(np.float64).sum())
+        assert n - 64 <= got <= n, (got, n)
+        assert np.array_equal(hist[..., 3], np.floor(hist[..., 3]))
+
+
+@pytest.mark.production_schedule
 def test_sample_count_is_exact_and_partial_units(native, built):
     """nsamples need not be a multiple of a unit; rejected samples are the only loss."""
     N = native
@@ -602,12 +641,12 @@ def test_packed_accumulation_equals_float4(native, built):
     density channel is identical, colour sums agree to float32 accumulation error --
     including bins that overflowed the 10-bit counter many times.
 
-    The float4 path adds every sample to a float32 running sum (round to nearest in the
-    L2 reduction unit, tools/micro/red_rounding.py); with n adds of nearly equal values the
-    rounding errors do not average out, so its relative error is bounded by n * 2^-25,
-    not by sqrt(n).  The packed path adds 8-bit integers exactly and touches the float
-    histogram once per ~32 samples, so it is the more exact of the two in very hot bins
-    (here up to ~6e5 samples per bin: measured 6e-3 against a 1.7e-2 bound)."""
+    A float32 running sum of n nearly equal addends drifts by up to n * 2^-25 (round to
+    nearest in the L2 reduction unit, tools/micro/red_rounding.py: the errors do not
+    average out).  The packed path adds 8-bit integers exactly and touches the float
+    histogram once per ~32 samples; the float4 path keeps integer sums exact by sweeping
+    (test_float4_sums_are_exact) except in bins above 1/1088 of all samples, like the
+    hottest ones here (~6e5 samples per bin of 2.9e8)."""
     N = native
     from cuburn_b200 import samples, render
     gnm = samples.g3()
@@ -638,6 +677,62 @@ def test_packed_accumulation_equals_float4(native, built):
         cool = a[..., 3][m] < 20000
         assert rel[cool].max() < 1e-3, (ch, float(rel[cool].max()))
     assert float(b[..., 3].sum()) <= w * h * spp
+
+
+def test_float4_sums_are_exact(native, built):
+    """The default (float4) accumulation adds integer palette levels and sweeps full bins
+    into a second grid (spill_sweep, device/iter_kernel.cuh), so its sums are exact where
+    a plain float32 running sum drifts by up to n * 2^-25.  Reference: the same sample set
+    launched in chunks small enough that no float add can round, added up in int64
+    (helpers.exact_level_sums).  Bins whose sums fit 24 bits must come out bit for bit as
+    float32(sum) * float32(1/255); hotter bins (here up to ~6e5 samples, sum ~1e8) may
+    round once per swept chunk in the spill grid and twice in cb_hist_finish."""
+    N = native
+    from cuburn_b200 import samples, render
+    from helpers import exact_level_sums
+    gnm = samples.g3()
+    w, h, spp = 160, 90, 20000
+    gprof, tc = still_profile(gnm, w, h, spp)
+    ts, td = frame_window(gprof, tc)
+    res = {}
+    for mode in ('exact', 'swept', 'unswept'):
+        rmgr = render.RenderManager(seed=17)
+        rmgr.accumulate, rmgr.hot_bins = 'float4', False
+        # the hottest bin takes 1/480 of the samples: sweep often enough for it
+        rmgr.spill_interval = 1 << 21
+        rmgr.spill = mode != 'unswept'
+        rdr = render.Renderer(gnm, gprof)
+        dim = rmgr.fb.set_dim(w, h)
+        rmgr._copy(rdr, gnm)
+        rmgr._interp(rdr, gnm, dim, ts, td)
+        if mode == 'exact':
+            res[mode] = exact_level_sums(N, rmgr, rdr, gnm, gprof, dim, tc)
+        else:
+            rmgr._iter(rdr, gnm, gprof, dim, tc)
+            rmgr.stream_a.synchronize()
+            res[mode] = N.from_device(rmgr.fb.d_front, (dim.ah, dim.astride, 4), np.float32)
+            if mode == 'swept':
+                fine = N.from_device(rmgr.fb.d_left, (dim.ah * dim.astride, 4), np.float32)
+                moved = N.from_device(rmgr.fb.d_right, (dim.ah * dim.astride, 4), np.float32)
+                assert fine.max() < 2.0 ** 24 and moved[:, 3].max() > 0
+        rmgr.fb.free()
+    exact, swept, unswept = res['exact'], res['swept'], res['unswept']
+    assert exact[..., 3].max() > 500000 and exact[..., 3].sum() <= w * h * spp
+    assert np.array_equal(swept[..., 3].astype(np.int64), exact[..., 3])
+    assert np.array_equal(unswept[..., 3].astype(np.int64), exact[..., 3])
+    k = np.float32(1.0 / 255.0)
+    small = (exact[..., :3] < 2 ** 24).all(axis=-1)
+    assert small.mean() > 0.5 and (~small).sum() > 10
+    want = exact[..., :3].astype(np.float32) * k            # one rounding each
+    assert np.array_equal(swept[..., :3][small], want[small])
+    big = ~small
+    ref = exact[..., :3][big] / 255.0
+    rel = np.abs(swept[..., :3][big].astype(np.float64) - ref) / ref
+    sweeps = w * h * spp / float(1 << 21)
+    assert rel.max() < 2.0 ** -22 + sweeps * 2.0 ** -25, float(rel.max())
+    # what the sweep is for: the plain running sums are off by orders of magnitude more
+    rel_plain = np.abs(unswept[..., :3][big].astype(np.float64) - ref) / ref
+    assert rel_plain.max() > 20 * rel.max(), (float(rel_plain.max()), float(rel.max()))
 
 
 def test_packed_path_with_motion_blur_and_final_xform(native, built):

@@ -25,6 +25,7 @@ def _oracle_frame(gnm, w, h, spp, tc, td, seed, threads=1):
     return o8.reshape(h, w, 4)
 
 
+@pytest.mark.production_schedule
 @pytest.mark.parametrize('gname,spp', [('G3', 1500), ('G6F', 4000)])
 def test_frame_psnr_vs_oracle(native, built, gname, spp):
     """T10.  Both sides are Monte-Carlo renders with different sample sets, so the
@@ -44,6 +45,7 @@ def test_frame_psnr_vs_oracle(native, built, gname, spp):
     assert val >= 40.0, val
 
 
+@pytest.mark.production_schedule
 def test_frame_psnr_vs_oracle_at_1080p(native, built):
     """BASELINE config 2 end to end against the oracle at its real size: the 1080p /
     2000 spp G6F frame through queue_frame (device interpolation, chaos game, filter
@@ -66,6 +68,7 @@ def test_frame_psnr_vs_oracle_at_1080p(native, built):
     assert val >= 40.0, val
 
 
+@pytest.mark.production_schedule
 def test_full_size_1080p_still_properties(native, built):
     """BASELINE config 2 at its real size (1920x1080, 2000 spp, G6F), where the oracle
     is too slow to run: properties that do not depend on the size.
@@ -119,6 +122,7 @@ def test_full_size_1080p_still_properties(native, built):
     assert psnr(frames[0][..., :3], frames[1][..., :3]) >= 40.0
 
 
+@pytest.mark.production_schedule
 @pytest.mark.parametrize('gname,w,h,spp,modes', [
     ('G6F', 3840, 2160, 4000, ('float4',)),                  # BASELINE config 3
     ('G24H', 7680, 4320, 2000, ('packed', 'float4'))])       # BASELINE config 5
