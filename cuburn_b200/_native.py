@@ -120,6 +120,8 @@ _SIGNATURES = {
                                POINTER(Dims), c_void_p]),
     'cb_hot_scan': (c_int, [c_uint64, c_uint64, c_uint64, c_uint64, c_uint64, c_int, c_float, c_float,
                             POINTER(Dims), c_void_p]),
+    'cb_sort_scratch_words': (c_int, [c_uint64, c_int, POINTER(c_uint64)]),
+    'cb_sort_pass': (c_int, [c_uint64, c_uint64, c_uint64, c_int, c_int, c_int, c_uint64, c_void_p]),
     'cb_yuv_to_rgb': (c_int, [c_uint64, c_uint64, POINTER(Dims), c_void_p]),
     'cb_den_blur': (c_int, [c_uint64, c_uint64, c_int, c_int, POINTER(c_float),
                             POINTER(Dims), c_void_p]),

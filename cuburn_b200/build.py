@@ -28,6 +28,7 @@ SOURCES = [
     ('cb_filters.cu', ['-use_fast_math']),
     ('cb_output.cu', ['-fmad=false']),
     ('cb_comm.cu', []),
+    ('cb_sort.cu', []),
 ]
 
 

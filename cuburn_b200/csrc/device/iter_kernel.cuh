@@ -472,7 +472,7 @@ cb_iter(const __grid_constant__ iter_args a) {
 
     mwc_st rng = a.seeds[gtid];
     point_set pt;
-#ifdef SPILL_DEBUG
+#ifdef CTA_TIMELINE
     if (tid == 0 && a.hot_tags) {
         unsigned long long t; unsigned int smid;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -636,7 +636,7 @@ cb_iter(const __grid_constant__ iter_args a) {
     for (int p = 0; p < POINTS; p++)
         a.points[p * POINT_STRIDE + gtid] = make_float4(pt.x[p], pt.y[p], pt.c[p], 0.0f);
     a.seeds[gtid] = rng;
-#ifdef SPILL_DEBUG
+#ifdef CTA_TIMELINE
     if (tid == 0 && a.hot_tags) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -231,6 +231,19 @@ int cb_hist_unswizzle(cb_dptr dst4, cb_dptr src4, int swizzle_bins,
 int cb_hist_finish(cb_dptr dst4, cb_dptr hist4, cb_dptr spill4, int swizzle_bins,
                    float level_scale, const cb_dims *dim, cb_stream s);
 
+/* ---- sorting (cuburn/code/sort.py:385-520, helpers/sortbench.cu) ----------
+ * One stable radix pass over 32-bit keys: dst receives the n keys of src grouped by the
+ * `bits` (1..8) bits above lo_bit, equal digits in their original order, so that
+ * least-significant-digit passes compose into a full sort (the reference's pass is
+ * unstable and its multi-pass sort marked broken, sort.py:437-441).  ignore_max drops
+ * keys equal to 0xffffffff (Sorter.sort's flag of the same name).  scratch: at least
+ * cb_sort_scratch_words(n, bits) 32-bit words; afterwards scratch[d * groups], with
+ * groups = ceil(n / 8192) (1 if n == 0), is the index in dst of the first key with digit
+ * d, and scratch[words - 8] the number of keys kept. */
+int cb_sort_scratch_words(uint64_t max_keys, int bits, uint64_t *words);
+int cb_sort_pass(cb_dptr dst, cb_dptr src, uint64_t n, int lo_bit, int bits,
+                 int ignore_max, cb_dptr scratch, cb_stream s);
+
 /* ---- filters (code/filters.py; host recipes in cuburn/filters.py) -------- */
 int cb_yuv_to_rgb(cb_dptr dst, cb_dptr src, const cb_dims *dim, cb_stream s);
 int cb_den_blur(cb_dptr dst1, cb_dptr src4, int pattern, int upsample,

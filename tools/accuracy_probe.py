@@ -25,6 +25,7 @@ for mode in ('exact', 'float4', 'float4 unswept', 'packed'):
     rmgr = render.RenderManager(seed=17)
     rmgr.accumulate, rmgr.hot_bins = ('packed' if mode == 'packed' else 'float4'), False
     rmgr.spill = mode != 'float4 unswept'
+    rmgr.schedule = 'static'           # the same sample set in every mode
     rdr = render.Renderer(gnm, gprof)
     dim = rmgr.fb.set_dim(w, h)
     rmgr._copy(rdr, gnm)

@@ -1,5 +1,5 @@
 """Start / end time and SM of every persistent CTA of one cb_iter launch (debug build of the
-module: -DSPILL_DEBUG writes %globaltimer / %smid per CTA).  python tools/cta_timeline.py [still|blur]"""
+module: -DCTA_TIMELINE writes %globaltimer / %smid per CTA).  python tools/cta_timeline.py [still|blur]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,7 +11,7 @@ w, h, spp = 1920, 1080, int(os.environ.get('SPP', 1000))
 gnm = samples.GENOMES[os.environ.get('GENOME', 'G6F')]()
 orig_gen = itergen.generate_source
 def gen(pk, params_const=False, extra_defines=None, **kw):
-    d = dict(extra_defines or {}); d['SPILL_DEBUG'] = '1'
+    d = dict(extra_defines or {}); d['CTA_TIMELINE'] = '1'
     return orig_gen(pk, params_const, extra_defines=d, **kw)
 itergen.generate_source = gen
 for fw in (0, 1e-9):
@@ -28,6 +28,7 @@ for fw in (0, 1e-9):
     render.N.IterArgs = IterArgs
     rmgr = render.RenderManager(seed=17)
     rmgr.accumulate, rmgr.hot_bins = 'float4', False
+    rmgr.schedule = os.environ.get('SCHED', 'dynamic')
     rdr = render.Renderer(gnm, gprof)
     dim = rmgr.fb.set_dim(w, h)
     rmgr._copy(rdr, gnm)
@@ -43,7 +44,7 @@ for fw in (0, 1e-9):
     tt = raw[4096:4096 + 1024 * 24].view(np.uint64).reshape(1024, 3)[:grid]
     t0 = tt[:, 0].min()
     st, en, sm = (tt[:, 0] - t0) / 1e6, (tt[:, 1] - t0) / 1e6, tt[:, 2].astype(int)
-    print('variant', 'still' if fw == 0 else 'blur', 'regs', info['num_regs'], 'ctas/sm', info['ctas_per_sm'], 'grid', grid)
+    print('schedule', rmgr.schedule, 'variant', 'still' if fw == 0 else 'blur', 'regs', info['num_regs'], 'ctas/sm', info['ctas_per_sm'], 'grid', grid)
     print(' kernel span %.2f ms; CTA start quantiles (ms) %s' % (en.max(), np.round(np.percentile(st, [0, 25, 50, 75, 90, 100]), 2).tolist()))
     print(' CTA end quantiles (ms) %s; run time quantiles %s' % (np.round(np.percentile(en, [0, 25, 50, 75, 90, 100]), 2).tolist(), np.round(np.percentile(en - st, [0, 25, 50, 75, 100]), 2).tolist()))
     late = st > 0.5
