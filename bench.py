@@ -550,6 +550,8 @@ def main():
             'algorithmic_bytes_per_bin': 804,
             'achieved': 804.0 * nbins / (filt_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
             'frac': 804.0 * nbins / (filt_ms * 1e-3) / 1e9 / peak, 'ms': filt_ms}
+    if getattr(rmgr.band_filter, 'shared', None) is not None:
+        rmgr.band_filter.shared.close()
     rmgr.fb.free()
     del rmgr, rdr
 
@@ -562,6 +564,8 @@ def main():
         for name in names:
             r = run_still(b, name, steps=max(3, min(5, args.steps)), warmup=3)
             st = r.pop('_state')
+            if getattr(st[0].band_filter, 'shared', None) is not None:
+                st[0].band_filter.shared.close()
             st[0].fb.free()
             del st
             r.pop('clocks', None)

@@ -150,12 +150,10 @@ def generate_source(packer, params_const=False, extra_defines=None, acc_packed=F
     out = ['// generated by cuburn_b200.code.itergen -- do not edit']
     for k, v in extra_defines.items():
         out.append('#define %s %s' % (k, v))
-    if not params_const and 'ITER_MIN_CTAS' not in extra_defines:
-        # Motion blur: the parameter block lives in shared memory and every value read
-        # from it needs a register; six CTAs of 40 registers beat eight of 32 (G24H, which
-        # spills at 32: 12.3 -> 11.1 ms; G6F 27.4 -> 26.6; G3 unchanged --
-        # profiles/r02_iter_variants.md)
-        out.append('#define ITER_MIN_CTAS 6')
+    # Eight CTAs of 32 registers for every variant.  (Under the static unit schedule six
+    # CTAs of 40 registers were faster for the motion-blur variant -- fewer, older warps
+    # suffered less from the schedulers' bias; with units claimed dynamically eight win:
+    # G6F 22.8 -> 22.3 ms, G24H 12.0 -> 11.4, profiles/r02_iter_variants_dyn.txt.)
     out += ['#include "mwc.cuh"', '#include "variations.cuh"', '']
     out.append('#define NSLOTS %d' % packer.nslots)
     out.append('#define POINTS %d' % points)
@@ -236,12 +234,15 @@ def best_points(packer, params_const):
         still             20.9 / 24.2             24.0 / 23.6     11.7 / 15.8
         motion blur       21.6 / 24.5             27.1 / 24.7     12.4 / 16.5
 
-    It pays where the kernel is bound by shared-memory parameter fetches (motion blur
-    of a mid-sized genome: -9 %, which brings the blurred frame within 3 % of the still),
-    does nothing for stills (parameters are constant-bank operands there), hurts light
-    genomes (their warps run in lockstep and the doubled burst of reductions after each
-    barrier stalls them) and heavy ones (twice the code no longer fits the instruction
-    cache).
+    That table is from the static unit schedule.  With units claimed dynamically
+    (profiles/r02_iter_variants_dyn.txt; every variant at eight CTAs per SM):
+
+        still             20.0 / 19.95            21.6 / 21.0     11.55 / 15.4
+        motion blur       20.3 / 19.9             25.4 / 22.3     11.4  / 15.3
+
+    It pays for mid-sized genomes in both variants (G6F: -2.6 % still, -12 % blurred,
+    which brings the blurred frame within 3 % of the still), is neutral for light genomes
+    and hurts heavy ones (twice the code no longer fits the instruction cache).
     """
     uses = sum(len(variations) for _, variations, _ in packer.xforms)
-    return 2 if (not params_const and not packer.xaos and 12 <= uses <= 32) else 1
+    return 2 if (not packer.xaos and 12 <= uses <= 32) else 1

@@ -227,7 +227,7 @@ int cb_module_set_global(cb_module m, const char *symbol, cb_dptr src, size_t by
 int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas, cb_stream s) {
     CB_REQUIRE(m && args, "null argument");
     CB_REQUIRE(grid_ctas > 0, "grid_ctas must be positive");
-    CB_REQUIRE(args->first_sample % 16384ull == 0, "first_sample must be unit aligned");
+    CB_REQUIRE(args->first_sample % 32768ull == 0, "first_sample must be unit aligned");
     CB_REQUIRE(args->nts > 0 && args->pal_rows > 0, "bad temporal sample counts");
     CB_REQUIRE(args->tickets || (!args->dynamic && !args->spill),
                "tickets scratch needed for dynamic units and for the spill sweep");

@@ -150,9 +150,9 @@ __device__ __forceinline__ float4 exch_zero_f32x4(float4 *addr) {
 
 // Split in two so that nobody waits for the counts: at the start of a unit every thread
 // asks for the counts of its bins of the window with 4-byte asynchronous copies into
-// shared memory (LDGSTS: no register, no scoreboard), at the end of the unit -- 64 rounds
+// shared memory (LDGSTS: no register, no scoreboard), at the end of the unit -- 128 rounds
 // later -- it looks at them.  A count read a unit ago only errs on the low side.
-#define SWEEP_MAX_WINDOW (2 * ITER_THREADS)
+#define SWEEP_MAX_WINDOW (4 * ITER_THREADS)
 
 __device__ __forceinline__ int sweep_bin(int base, int i, int nbins) {
     const int b = base + i;

@@ -7,7 +7,7 @@
 #define ITER_THREADS 256
 #endif
 #ifndef UNIT_ROUNDS
-#define UNIT_ROUNDS 64
+#define UNIT_ROUNDS 128
 #endif
 #ifndef ITER_MIN_CTAS
 #define ITER_MIN_CTAS 8        // 32 registers, 64 warps / SM: measured fastest (profiles/r01_iter_variants.md)

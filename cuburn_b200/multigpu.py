@@ -320,6 +320,14 @@ class SharedFrame(object):
             self.array = None
             self._mm = None
 
+    def __del__(self):
+        # a mapping that goes away while still registered poisons its address range: the
+        # next segment mapped there fails to register ("already mapped")
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 def gather_host_bands(frame, rank, world, root=0):
     """gloo/CPU twin of BandFilter's gather: `frame` is [aheight, ...]; the root's copy

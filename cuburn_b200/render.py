@@ -23,9 +23,9 @@ from .genome.util import palette_decode
 RenderedImage = namedtuple('RenderedImage', 'buf idx gpu_time')
 Dimensions = N.Dims
 
-# Samples one CTA processes per work unit (256 threads x 64 rounds); sample
+# Samples one CTA processes per work unit (256 threads x 128 rounds); sample
 # ranges handed to cb_iterate are aligned to this.
-UNIT_SAMPLES = 16384
+UNIT_SAMPLES = 32768
 ITER_THREADS = 256
 # layout of RenderManager.d_hot (cb_hot_scan): scratch, tags, counters
 HOT_TAGS_OFF = 8 * 1024 * 8
@@ -427,7 +427,7 @@ class RenderManager(object):
     spill = True
     spill_interval = 1 << 26
     spill_count = 4096.0
-    spill_max_window = 512          # SWEEP_MAX_WINDOW of device/iter_kernel.cuh
+    spill_max_window = 1024         # SWEEP_MAX_WINDOW of device/iter_kernel.cuh
 
     def _spill_window(self, nbins, n):
         """Bins every unit examines, for a launch of n samples."""
@@ -463,7 +463,7 @@ class RenderManager(object):
     # persistent CTAs per cb_iterate launch; None: fill the GPU at the module's occupancy
     iter_grid = None
 
-    # How units of 16384 samples are dealt out to the persistent CTAs.  'dynamic': a CTA
+    # How units of 32768 samples are dealt out to the persistent CTAs.  'dynamic': a CTA
     # claims its next unit when it is ready for it -- the CTAs of an SM run at very
     # different speeds (the warp schedulers favour the oldest warps), and with static
     # ownership the slow ones finish the launch alone.  'static': CTA b runs units

@@ -180,7 +180,7 @@ typedef struct {
                                 that receives the bins the in-kernel sweep finds full, so
                                 that the float sums in hist stay below 2^24 and exact
                                 (the reference's spill, iter.py:359-407, done by sweeping) */
-    int32_t spill_bins;      /* bins every unit of 16384 samples examines */
+    int32_t spill_bins;      /* bins every unit of 32768 samples examines */
     float spill_count;       /* a bin holding >= this many samples is moved to spill */
     cb_dptr tickets;         /* uint32 [2] scratch, zeroed by cb_iterate: unit and sweep counters */
     int32_t dynamic;         /* 0: CTA b runs units b, b + grid_ctas, ... (the sample set is a
@@ -191,7 +191,7 @@ typedef struct {
 } cb_iter_args;
 /* The chaos game (iter kernel, code/iter.py:157-418): nsamples iterations
  * accumulated into hist.  grid_ctas persistent CTAs of 256 threads; work is
- * split in units of 16384 samples and first_sample must be unit aligned. */
+ * split in units of 32768 samples and first_sample must be unit aligned. */
 int cb_iterate(cb_module m, const cb_iter_args *args, int grid_ctas,
                cb_stream s);
 
