@@ -533,9 +533,11 @@ def main():
             'what': ('8 B packed-u64 accumulate per sample into a grid far larger than L2: '
                      'HBM sector read-modify-write' if packed else
                      'one red.global.add.v4.f32 per sample into an L2-resident float4 grid; peak '
-                     '= scattered reductions of the same size into the same grid, measured in '
-                     'this run (L2 request rate; the histogram never leaves L2, so DRAM '
-                     'traffic is ~0 and HBM does not bound the kernel)'),
+                     '= uniformly scattered reductions of the same size into the same grid, '
+                     'measured in this run (L2 request rate; the histogram never leaves L2, so '
+                     'DRAM traffic is ~0 and HBM does not bound the kernel).  A flame\'s '
+                     'addresses are more concentrated than a uniform scatter, so the kernel can '
+                     'sit a few per cent above this figure'),
             'hbm': {'algorithmic_bytes_per_sample': algo, 'achieved': gbs, 'peak': peak,
                     'unit': 'GB/s', 'frac': gbs / peak, 'peak_source': peak_src},
             'l2_atomic': {'achieved': kernel_rate, 'peak': red_peak, 'unit': 'reductions/s',
