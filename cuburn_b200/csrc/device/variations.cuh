@@ -9,7 +9,18 @@
 // module is built with --use_fast_math (sin/cos/ex2/lg2/rcp/rsq -> MUFU.*).
 #pragma once
 
+// VFN_NOINLINE (experiment, off): one copy of every variation body per module, called,
+// instead of one per use.  A heavy genome (G24H: 72 variation uses in 24 xforms) compiles to
+// 0.5 MB of straight-line code that every warp walks through a different part of, and ncu
+// shows its warps waiting for instructions as often as for anything else (stall
+// no_instruction 7.7 per issue at 8K).  Calls shrink the module to 0.34 MB but pass the
+// accumulators and the RNG through the stack: G24H 11.37 -> 11.26 ms (nothing), G6F 21.6 ->
+// 49.4 ms.  Measured and rejected (profiles/r02_iter_variants_dyn.txt).
+#ifdef VFN_NOINLINE
+#define VFN __device__ __noinline__ void
+#else
 #define VFN __device__ __forceinline__ void
+#endif
 
 #define CB_PI      3.14159274101257f
 #define CB_PI_2    1.57079637050629f
