@@ -90,8 +90,11 @@ struct iter_args {
 // level * (1 / 255) (cb_interp_palette), so the contribution is bit-identical.  Pays
 // where the kernel is bound by L1TEX wavefronts (motion blur: parameters in shared
 // memory), costs issue slots where it is not (profiles/r02_iter_variants.md).
+// Since the kernel became L1TEX-bound at 86 % (dynamic units, two points per thread) it also
+// pays for the still variant with two points: G6F 21.47 -> 21.03 ms; with one point it still
+// costs (21.59 -> 21.9), profiles/r02_iter_variants_dyn.txt.
 #ifndef PAL_COMPACT
-#define PAL_COMPACT (HOT_BINS || !PARAMS_CONST)
+#define PAL_COMPACT (HOT_BINS || !PARAMS_CONST || POINTS == 2)
 #endif
 #if ACC_PACKED
 #undef PAL_COMPACT
