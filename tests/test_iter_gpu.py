@@ -735,6 +735,50 @@ def test_float4_sums_are_exact(native, built):
     assert rel_plain.max() > 20 * rel.max(), (float(rel_plain.max()), float(rel.max()))
 
 
+def test_float4_sums_are_exact_at_1080p(native, built):
+    """The same at a benchmark size (G6F 1080p, slice-balancing layout, default sweep
+    interval): the hottest bin takes 0.07 % of the samples, below the 1/1088 up to which
+    the default sweeps keep every add exact -- so every bin must equal the int64 reference
+    to the two roundings of cb_hist_finish (sums above 2^24 live in the spill grid and may
+    round once per swept chunk)."""
+    N = native
+    from cuburn_b200 import samples, render
+    from helpers import exact_level_sums
+    gnm = samples.g6f()
+    w, h, spp = 1920, 1080, 300
+    gprof, tc = still_profile(gnm, w, h, spp)
+    ts, td = frame_window(gprof, tc)
+    res = {}
+    for mode in ('exact', 'swept'):
+        rmgr = render.RenderManager(seed=23)
+        rmgr.hot_bins = False
+        rdr = render.Renderer(gnm, gprof)
+        dim = rmgr.fb.set_dim(w, h)
+        assert rmgr._use_swizzle(dim.ah * dim.astride) and not rmgr._use_packed(dim.ah * dim.astride)
+        rmgr._copy(rdr, gnm)
+        rmgr._interp(rdr, gnm, dim, ts, td)
+        if mode == 'exact':
+            res[mode] = exact_level_sums(N, rmgr, rdr, gnm, gprof, dim, tc, waves_per_chunk=2)
+        else:
+            rmgr._iter(rdr, gnm, gprof, dim, tc)
+            rmgr.stream_a.synchronize()
+            res[mode] = N.from_device(rmgr.fb.d_front, (dim.ah, dim.astride, 4), np.float32)
+            fine = N.from_device(rmgr.fb.d_left, (dim.ah * dim.astride, 4), np.float32)
+            assert fine.max() < 2.0 ** 24          # nothing was left to round
+        rmgr.fb.free()
+    exact, swept = res['exact'], res['swept']
+    assert exact[..., 3].max() > 200000
+    assert np.array_equal(swept[..., 3].astype(np.int64), exact[..., 3])
+    k = np.float32(1.0 / 255.0)
+    small = (exact[..., :3] < 2 ** 24).all(axis=-1)
+    assert np.array_equal(swept[..., :3][small], (exact[..., :3].astype(np.float32) * k)[small])
+    big = ~small
+    assert big.sum() > 0
+    ref = exact[..., :3][big] / 255.0
+    rel = np.abs(swept[..., :3][big].astype(np.float64) - ref) / ref
+    assert rel.max() < 2.0 ** -22 + 16 * 2.0 ** -25, float(rel.max())
+
+
 def test_packed_path_with_motion_blur_and_final_xform(native, built):
     """Packed accumulation through queue_frame (forced) vs the float4 frame."""
     from cuburn_b200 import samples, render, profile
