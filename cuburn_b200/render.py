@@ -594,9 +594,11 @@ class RenderManager(object):
                 seeds[:] = make_rank_seeds(rank, world, int(frame_seed), self.fb.nstreams)
             else:
                 seeds[:] = mwc.make_seeds(self.fb.nstreams, host_seed=int(frame_seed))
-            # the seed table is shared with the previous frame (which ran on stream_b
-            # and still dithers its output from it): order this upload after it
-            self.stream_a.wait_for_event(N.Event().record(self.stream_b))
+            # the seed table is shared with the previous frame (which ran on stream_b and
+            # dithers its output from it): order this upload after that frame's conversion
+            # -- not after its D2H copy, which only reads the converted frame
+            if self.filt_evt:
+                self.stream_a.wait_for_event(self.filt_evt)
             N.memcpy_htod(self.fb.d_seeds, seeds, self.stream_a)
             self._pinned.append((seeds,))
         dim = self.fb.set_dim(gprof.width, gprof.height, self.stream_b)

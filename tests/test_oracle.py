@@ -206,4 +206,5 @@ def test_bench_cpu_filter_baseline_reports_every_stage():
     r = bench.cpu_filter_rates(w=96, h=54)
     assert set(r['value']) == {'yuv_to_rgb', 'bilateral (8 directions)', 'logscale', 'smearclip',
                                'chain'}
-    assert all(v > 0 for v in r['value'].values()) and r['cores'] == 1 and r['kind'] == 'port'
+    assert all(v > 0 for v in r['value'].values()) and r['kind'] == 'port'
+    assert r['cores'] == (os.cpu_count() or 1)
