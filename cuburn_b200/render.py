@@ -411,6 +411,7 @@ class RenderManager(object):
     hot_trigger = 1.0 / 512
     hot_pilot = 64
     hot_min_waves = 4               # frames shorter than this many waves of units: never
+    hot_recheck = 8                 # 'auto', genome without hot bins: pilot every n-th frame
 
     # Exact sums on the float4 path (device/iter_kernel.cuh, spill_sweep): the kernel adds
     # integer palette levels, and sweeps the grid once per ``spill_interval`` samples,
@@ -484,6 +485,12 @@ class RenderManager(object):
                 rdr.hot = bool(count[0] > 0)
         if rdr.hot is None:
             return True, None               # first frame of this genome: probe and wait
+        if not rdr.hot:
+            # nothing hot last time: look again every hot_recheck frames only (the pilot
+            # splits the frame into two launches, ~0.1 ms per 1080p frame)
+            rdr._hot_quiet = getattr(rdr, '_hot_quiet', 0) + 1
+            if rdr._hot_quiet % self.hot_recheck:
+                return False, False
         return True, rdr.hot
 
     def _iter(self, rdr, gnm, gprof, dim, tc):
