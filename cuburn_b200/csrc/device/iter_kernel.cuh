@@ -165,6 +165,9 @@ __device__ __forceinline__ int sweep_bin(int base, int i, int nbins) {
 #ifndef SWEEP_HINT
 #define SWEEP_HINT 0
 #endif
+#ifndef SWEEP_BLOCKING
+#define SWEEP_BLOCKING 0
+#endif
 __device__ __forceinline__ void sweep_begin(float *counts, const float4 *hist, int nbins, int base,
                                             int window, int tid) {
 #if SWEEP_HINT
@@ -179,7 +182,19 @@ __device__ __forceinline__ void sweep_begin(float *counts, const float4 *hist, i
     for (int k = 0; k < SWEEP_MAX_WINDOW / ITER_THREADS; k++) {
         const int i = tid + k * ITER_THREADS;
         if (i < window)
-#if SWEEP_HINT
+#if SWEEP_BLOCKING == 1
+        {
+            float v;
+            asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(&hist[sweep_bin(base, i, nbins)].w));
+            counts[i] = v;
+        }
+#elif SWEEP_BLOCKING == 2
+        {
+            float v;
+            asm volatile("ld.global.lu.f32 %0, [%1];" : "=f"(v) : "l"(&hist[sweep_bin(base, i, nbins)].w));
+            counts[i] = v;
+        }
+#elif SWEEP_HINT
             asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;"
                          :: "r"((unsigned int)__cvta_generic_to_shared(counts + i)),
                             "l"(&hist[sweep_bin(base, i, nbins)].w), "l"(pol) : "memory");

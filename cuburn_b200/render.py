@@ -420,11 +420,11 @@ class RenderManager(object):
     # to collect 65793 - spill_count samples between two sweeps (1/1088 of all samples at
     # the defaults) before a float add rounds; much hotter bins are what ``hot_bins`` is for.
     # Grids that do not stay L2-resident are swept less often -- a sweep pulls every sector of
-    # the grid through L2, the untouched background included, and costs ~0.5 % of a 4K /
-    # 500 spp launch (measured, profiles/r02_schedule_and_sweep.md) -- so there the bound on
-    # a bin's rounding error only improves by the number of sweeps.  False: no sweeps (sums
-    # round like any float32 running sum, relative error up to n * 2^-25 for a bin of n
-    # samples).
+    # the grid through L2, the untouched background included, as scattered DRAM traffic:
+    # 0.26 ms per sweep of the 4K grid (measured, tools/stage_parts.py), 10 x its streaming
+    # time -- so there the bound on a bin's rounding error only improves by the number of
+    # sweeps (8 per 4K / 4000 spp frame, ~1 % of its time).  False: no sweeps (sums round like
+    # any float32 running sum, relative error up to n * 2^-25 for a bin of n samples).
     spill = True
     spill_interval = 1 << 26
     spill_count = 4096.0
@@ -439,7 +439,7 @@ class RenderManager(object):
         if not hasattr(self, '_l2_bytes'):
             self._l2_bytes = N.device_info(N._initialised or 0)['l2_bytes']
         if 16 * nbins > 0.6 * self._l2_bytes:
-            sweeps = min(sweeps, max(1, int(0.005 * n / nbins)))
+            sweeps = min(sweeps, max(1, int(0.002 * n / nbins)))
         return int(min(-(-nbins * sweeps // nunits), self.spill_max_window, nbins))
 
     def _launch_iter(self, mod, rdr, info, d_acc, swz, dim, first, n, total, fuse, packed,
