@@ -162,47 +162,17 @@ __device__ __forceinline__ int sweep_bin(int base, int i, int nbins) {
     return b >= nbins ? b - nbins : b;
 }
 
-#ifndef SWEEP_HINT
-#define SWEEP_HINT 0
-#endif
-#ifndef SWEEP_BLOCKING
-#define SWEEP_BLOCKING 0
-#endif
+// (Streaming / last-use / evict-first hints on these loads were measured at 4K, where a sweep
+// drags the whole grid through L2: no difference, profiles/r02_schedule_and_sweep.md.)
 __device__ __forceinline__ void sweep_begin(float *counts, const float4 *hist, int nbins, int base,
                                             int window, int tid) {
-#if SWEEP_HINT
-    unsigned long long pol;
-#if SWEEP_HINT == 1
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-#else
-    asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
-#endif
-#endif
 #pragma unroll
     for (int k = 0; k < SWEEP_MAX_WINDOW / ITER_THREADS; k++) {
         const int i = tid + k * ITER_THREADS;
         if (i < window)
-#if SWEEP_BLOCKING == 1
-        {
-            float v;
-            asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(&hist[sweep_bin(base, i, nbins)].w));
-            counts[i] = v;
-        }
-#elif SWEEP_BLOCKING == 2
-        {
-            float v;
-            asm volatile("ld.global.lu.f32 %0, [%1];" : "=f"(v) : "l"(&hist[sweep_bin(base, i, nbins)].w));
-            counts[i] = v;
-        }
-#elif SWEEP_HINT
-            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;"
-                         :: "r"((unsigned int)__cvta_generic_to_shared(counts + i)),
-                            "l"(&hist[sweep_bin(base, i, nbins)].w), "l"(pol) : "memory");
-#else
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                          :: "r"((unsigned int)__cvta_generic_to_shared(counts + i)),
                             "l"(&hist[sweep_bin(base, i, nbins)].w) : "memory");
-#endif
     }
 }
 
