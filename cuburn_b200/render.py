@@ -419,6 +419,8 @@ class RenderManager(object):
     # stays exact while it is below 2^24 = 65793 samples of level 255, so a bin would have
     # to collect 65793 - spill_count samples between two sweeps (1/1088 of all samples at
     # the defaults) before a float add rounds; much hotter bins are what ``hot_bins`` is for.
+    # (The CTAs of a wave begin their units -- and load their windows -- together, so sweeps
+    # more frequent than one per wave of the grid, 1024 x 32768 = 2^25 samples, add nothing.)
     # Grids that do not stay L2-resident are swept less often -- a sweep pulls every sector of
     # the grid through L2, the untouched background included, as scattered DRAM traffic:
     # 0.26 ms per sweep of the 4K grid (measured, tools/stage_parts.py), 10 x its streaming

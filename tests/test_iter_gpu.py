@@ -698,15 +698,18 @@ def test_float4_sums_are_exact(native, built):
     for mode in ('exact', 'swept', 'unswept'):
         rmgr = render.RenderManager(seed=17)
         rmgr.accumulate, rmgr.hot_bins = 'float4', False
-        # the hottest bin takes 1/480 of the samples: sweep often enough for it
+        # the hottest bin takes 1/480 of the samples: sweep often enough for it.  The CTAs of
+        # a wave begin their units together, so sweeps cannot usefully be more frequent than
+        # waves: a small grid makes a wave (64 x 32768 samples) as short as the interval
         rmgr.spill_interval = 1 << 21
+        rmgr.iter_grid = 64
         rmgr.spill = mode != 'unswept'
         rdr = render.Renderer(gnm, gprof)
         dim = rmgr.fb.set_dim(w, h)
         rmgr._copy(rdr, gnm)
         rmgr._interp(rdr, gnm, dim, ts, td)
         if mode == 'exact':
-            res[mode] = exact_level_sums(N, rmgr, rdr, gnm, gprof, dim, tc)
+            res[mode] = exact_level_sums(N, rmgr, rdr, gnm, gprof, dim, tc, waves_per_chunk=8)
         else:
             rmgr._iter(rdr, gnm, gprof, dim, tc)
             rmgr.stream_a.synchronize()
