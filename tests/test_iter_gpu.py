@@ -442,6 +442,29 @@ def test_hot_bins_are_exact_and_found_automatically(native, built):
     assert i4['hot'] is False
 
 
+def test_hot_bins_with_two_points_per_thread(native, built, monkeypatch):
+    """The hot-bin variant of a module that carries two trajectories per thread (what a
+    mid-sized genome with a bright core compiles to): same density as the plain variant with
+    two points, sample for sample."""
+    from cuburn_b200 import samples, render
+    monkeypatch.setattr(render.Renderer, 'points', 2)
+    gnm = samples.GENOMES['G2M']()
+    w, h, spp = 1920, 1080, 100
+    grid = 148 * 6
+    plain, _, i0 = _device_hist(native, gnm, w, h, spp, 9, hot_bins=False, grid=grid)
+    hot, _, i1 = _device_hist(native, gnm, w, h, spp, 9, hot_bins=True, grid=grid)
+    assert (i0['hot'], i1['hot']) == (False, True)
+    assert np.array_equal(plain[..., 3], hot[..., 3])
+    assert plain[..., 3].sum() > 0.5 * w * h * spp
+    m = plain[..., 3] > 0
+    for ch in range(3):
+        # the plain path rounds in bins far above the sweep's limit (G2M's hottest bin takes
+        # 0.7 % of the samples), the hot path holds integer sums there
+        rel = np.abs(plain[..., ch][m] - hot[..., ch][m]) / np.maximum(plain[..., ch][m], 1e-3)
+        bound = 1e-5 + plain[..., 3][m].astype(np.float64) * 2.0 ** -25
+        assert (rel <= bound).all(), (ch, float((rel / bound).max()))
+
+
 @pytest.mark.production_schedule
 def test_dynamic_schedule_draws_every_unit_once(native, built):
     """The shipped schedule hands units to CTAs on demand (which stream draws which unit
