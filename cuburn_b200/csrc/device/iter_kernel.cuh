@@ -120,9 +120,30 @@ struct iter_args {
 // iter_args::points holds POINTS planes of this many trajectories (= RNG streams)
 #define POINT_STRIDE 262144
 
+// RED_POLICY 1: the per-sample reductions carry an L2 "evict last" priority.  A scattered
+// reduction stream into a grid that is a large fraction of L2 runs up to 46 % faster with it
+// (tools/red_policy_microbench.py: uniform addresses, 100 MiB grid 1.24e11 -> 1.82e11/s,
+// 120 MiB 0.99e11 -> 1.45e11/s; nothing changes for grids up to half of L2): without the
+// hint the cache keeps writing dirty sectors back that the next reduction dirties again.
+#ifndef RED_POLICY
+#define RED_POLICY 0
+#endif
+__device__ __forceinline__ unsigned long long red_policy() {
+    unsigned long long pol = 0ull;
+#if RED_POLICY
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+
 __device__ __forceinline__ void red_add_f32x4(float4 *addr, float4 v) {
+#if RED_POLICY
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(red_policy()) : "memory");
+#else
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
 }
 
 // ---- exact sums in a float4 histogram -------------------------------------------------
@@ -207,7 +228,12 @@ __device__ __forceinline__ void sweep_end(const float *counts, float4 *hist, flo
 __device__ __forceinline__ void accumulate_packed(unsigned long long *cell, float4 *hist,
                                                   unsigned long long v, bool drain) {
     if (!drain) {
+#if RED_POLICY
+        asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;"
+                     :: "l"(cell), "l"(v), "l"(red_policy()) : "memory");
+#else
         asm volatile("red.global.add.u64 [%0], %1;" :: "l"(cell), "l"(v) : "memory");
+#endif
         return;
     }
     unsigned long long old = atomicExch(cell, 0ull);

@@ -220,10 +220,11 @@ class Renderer(object):
 
     @classmethod
     def compile(cls, gnm, arch=None, keep=False, params_const=False, acc_packed=False,
-                hot_bins=False):
+                hot_bins=False, big_grid=False):
         pk = itergen.GenomePacker(gnm)
         src = itergen.generate_source(pk, params_const, acc_packed=acc_packed, hot_bins=hot_bins,
-                                      points=cls._points(pk, params_const))
+                                      points=cls._points(pk, params_const),
+                                      extra_defines={'RED_POLICY': '1'} if big_grid else None)
         mod = cls._module(src)
         if keep:
             import os, tempfile
@@ -249,14 +250,18 @@ class Renderer(object):
     def cubin(self):
         return self.mod.cubin
 
-    def variant(self, params_const, acc_packed=False, hot_bins=False):
+    def variant(self, params_const, acc_packed=False, hot_bins=False, big_grid=False):
         """The iterate module for (parameters in __constant__ memory?, packed u64
-        accumulation?, private shared-memory cells for hot bins?), compiled on first
-        use."""
+        accumulation?, private shared-memory cells for hot bins?, reductions with an L2
+        evict-last priority -- for grids that are a large part of L2 or exceed it?),
+        compiled on first use."""
         key = (bool(params_const), bool(acc_packed), bool(hot_bins))
+        if big_grid:
+            key += (True,)
         if key not in self._variants:
             self._variants[key] = self.compile(self._gnm_structure, params_const=key[0],
-                                               acc_packed=key[1], hot_bins=key[2])[2]
+                                               acc_packed=key[1], hot_bins=key[2],
+                                               big_grid=bool(big_grid))[2]
         return self._variants[key]
 
     @property
@@ -377,11 +382,15 @@ class RenderManager(object):
     # neighbouring bins destroys sector locality.
     swizzle = 'auto'
 
+    def _l2(self):
+        """Bytes of L2 on this device."""
+        if not hasattr(self, '_l2_cached'):
+            self._l2_cached = N.device_info(N._initialised or 0)['l2_bytes']
+        return self._l2_cached
+
     def _use_swizzle(self, nbins):
         if self.swizzle == 'auto':
-            if not hasattr(self, '_l2_bytes'):
-                self._l2_bytes = N.device_info(N._initialised or 0)['l2_bytes']
-            return 16 * nbins <= 1.5 * self._l2_bytes
+            return 16 * nbins <= 1.5 * self._l2()
         return bool(self.swizzle)
 
     # How samples are accumulated.  'auto': float4 reductions straight into the
@@ -393,9 +402,7 @@ class RenderManager(object):
 
     def _use_packed(self, nbins):
         if self.accumulate == 'auto':
-            if not hasattr(self, '_l2_bytes'):
-                self._l2_bytes = N.device_info(N._initialised or 0)['l2_bytes']
-            return 16 * nbins > 1.5 * self._l2_bytes
+            return 16 * nbins > 1.5 * self._l2()
         return self.accumulate == 'packed'
 
     # A bin that collects more than ~0.4 % of the samples is bound by the rate of one
@@ -438,9 +445,7 @@ class RenderManager(object):
             return 0
         nunits = (n + UNIT_SAMPLES - 1) // UNIT_SAMPLES
         sweeps = max(1, -(-n // self.spill_interval))
-        if not hasattr(self, '_l2_bytes'):
-            self._l2_bytes = N.device_info(N._initialised or 0)['l2_bytes']
-        if 16 * nbins > 0.6 * self._l2_bytes:
+        if 16 * nbins > 0.6 * self._l2():
             sweeps = min(sweeps, max(1, int(0.002 * n / nbins)))
         return int(min(-(-nbins * sweeps // nunits), self.spill_max_window, nbins))
 
@@ -515,7 +520,10 @@ class RenderManager(object):
         # that reads one parameter block from __constant__ memory
         still = gprof.frame_width(tc) == 0
         nunits = (n + UNIT_SAMPLES - 1) // UNIT_SAMPLES
-        mod = rdr.variant(still, packed)
+        # grids from about half of L2 up: reductions carry an evict-last priority (measured:
+        # 4K float4 -4 %, 8K packed cells -3 %, 1080p +2 % -- so not there)
+        big = (8 if packed else 16) * nbins > 0.5 * self._l2()
+        mod = rdr.variant(still, packed, big_grid=big)
         grid = self.iter_grid or rdr.grid_ctas(self.fb.nstreams, mod)
         pilot, hot = self._hot_decision(rdr, nunits, packed, grid)
         if still:
@@ -547,7 +555,7 @@ class RenderManager(object):
                 (UNIT_SAMPLES // (ITER_THREADS * ppt))
             first, n, fuse = first + npilot, n - npilot, 0
         if hot:
-            mod = rdr.variant(still, packed, True)
+            mod = rdr.variant(still, packed, True, big_grid=big)
             if still:
                 mod.set_global('c_params', info.d_params.ptr, 4 * rdr.packer.nslots, s)
         if n > 0:
