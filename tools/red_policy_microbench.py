@@ -17,6 +17,12 @@ red_policy(float4 *hist, mwc_st *seeds, unsigned int nbins, int rounds) {
     unsigned long long pol;
 #if POLICY == 1
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#elif POLICY == 4
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(pol));
+#elif POLICY == 5
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.25;" : "=l"(pol));
+#elif POLICY == 6
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(pol));
 #elif POLICY == 2
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 #else
@@ -41,17 +47,22 @@ sms = N.device_info(0)['sm_count']
 names, hdrs = itergen.load_headers()
 seeds = N.to_device(mwc.make_seeds(262144, host_seed=5))
 grid, rounds = sms * 6, 8192
-big = N.DeviceBuffer(192 << 20)
-for policy, pname in ((0, 'none'), (1, 'evict_last'), (2, 'evict_first'), (3, 'evict_unchanged')):
+big = N.DeviceBuffer(320 << 20)
+POLICIES = ((0, 'none'), (1, 'evict_last'), (2, 'evict_first'), (3, 'evict_unchanged'),
+            (4, 'evict_last 0.5 / evict_first'), (5, 'evict_last 0.25 / evict_first'), (6, 'evict_last 0.5 / normal'))
+SIZES = [int(x) for x in os.environ.get('SIZES', '33,66,100,120,130,160').split(',')]
+if os.environ.get('POLICIES'):
+    POLICIES = [p for p in POLICIES if str(p[0]) in os.environ['POLICIES'].split(',')]
+for policy, pname in POLICIES:
     try:
         mod = N.Module(SRC, 'redpol.cu', hdrs, names, ['--gpu-architecture=sm_100a', '--std=c++17', '-DPOLICY=%d' % policy])
     except Exception as e:
         print(json.dumps(dict(policy=pname, error=str(e)[:200]))); continue
-    for mb in (33, 66, 100, 120, 130, 160):
+    for mb in SIZES:
         nbins = (mb << 20) // 16
         best = 1e9
         for rep in range(3):
-            N.fill32(big, (192 << 20) // 4, 0)
+            N.fill32(big, (320 << 20) // 4, 0)
             e0, e1 = N.Event(), N.Event()
             e0.record(None)
             mod.launch('red_policy', (grid,), (256,), [C.c_uint64(big.ptr), C.c_uint64(seeds.ptr), C.c_uint(nbins), C.c_int(rounds)])
