@@ -575,7 +575,7 @@ def main():
             del st
             r.pop('clocks', None)
             extra[name] = r
-        extra['anim1080'] = run_anim(b, 'anim1080', frames_per_gpu=max(8, min(24, args.steps)),
+        extra['anim1080'] = run_anim(b, 'anim1080', frames_per_gpu=24,
                                      warmup=3)
 
     cpu = cpu_filters = None
