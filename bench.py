@@ -336,7 +336,8 @@ def run_still(b, name, steps, warmup, sampler=None):
     reducer = shared = None
     if b.world > 1:
         banded = args.filter_shard == 'band'
-        reducer = multigpu.HistReducer(root=None if banded else 0, comm=b.comm)
+        reducer = multigpu.HistReducer(root=None if banded else 0, comm=b.comm,
+                                       integer_sums=True)
         rmgr.hist_hook = reducer
         if banded:
             if args.band_output == 'shared':
@@ -357,7 +358,7 @@ def run_still(b, name, steps, warmup, sampler=None):
         rmgr._iter(rdr, gnm, gprof, dim, tc)
         ev_iter1.record(s)
         if reducer is not None:
-            reducer(rmgr.fb, dim, s)
+            rmgr._combine(dim)              # the reducer (rmgr.hist_hook) + the 1/255 scale
         if rmgr.band_filter is not None or b.rank == 0:
             rmgr._filter(rdr, gprof, dim, tc)
         if shared is not None:

@@ -566,15 +566,33 @@ class RenderManager(object):
             # and the main launch may wait on the host); the next frame picks it up
             N.memcpy_dtoh(probe, N.DeviceSlice(self.d_hot, HOT_COUNT_OFF, 4), s)
             self._hot_probe = (N.Event().record(s), probe, rdr)
+        self._raw_levels = False
         if packed:
             N.check(N.lib().cb_flush_packed(self.fb.d_front.ptr, self.fb.d_left.ptr,
                                             N.byref(dim), s.handle))
         else:
+            # a multi-GPU hook that wants to sum the integer levels exactly gets them
+            # unscaled; _combine divides by 255 after it
+            raw = self._raw_levels = bool(getattr(self.hist_hook, 'integer_sums', False))
             N.check(N.lib().cb_hist_finish(
                 self.fb.d_front.ptr, int(d_acc), self.fb.d_right.ptr if self.spill else 0, swz,
-                np.float32(1.0 / 255.0), N.byref(dim), s.handle))
+                np.float32(1.0 if raw else 1.0 / 255.0), N.byref(dim), s.handle))
         self.last_iter_samples = n_frame
         self.last_iter_hot = bool(hot)
+
+    # -- combine (multi-GPU stills) -----------------------------------------------------
+    _raw_levels = False
+
+    def _combine(self, dim):
+        """Run ``hist_hook`` (the per-GPU histograms become one) and bring the result to
+        the (sum / 255, count) form if the iterate stage left integer level sums for it."""
+        if self.hist_hook is not None:
+            self.hist_hook(self.fb, dim, self.stream_a)
+        if self._raw_levels:
+            N.check(N.lib().cb_hist_finish(self.fb.d_front.ptr, self.fb.d_front.ptr, 0, 0,
+                                           np.float32(1.0 / 255.0), N.byref(dim),
+                                           self.stream_a.handle))
+            self._raw_levels = False
 
     # -- filter ----------------------------------------------------------------------
     # multi-GPU stills: a multigpu.BandFilter makes every GPU filter a band of rows
@@ -633,9 +651,8 @@ class RenderManager(object):
             self.stream_a.wait_for_event(self.filt_evt)
         self._interp(rdr, gnm, dim, ts, td)
         self._iter(rdr, gnm, gprof, dim, tc)
-        if self.hist_hook is not None:
-            # multi-GPU stills: combine per-GPU histograms before filtering
-            self.hist_hook(self.fb, dim, self.stream_a)
+        # multi-GPU stills: combine per-GPU histograms before filtering
+        self._combine(dim)
         if self.copy_evt:
             self.stream_a.wait_for_event(self.copy_evt)
         self._filter(rdr, gprof, dim, tc)

@@ -27,6 +27,7 @@ dim = rmgr.fb.set_dim(w, h)
 shape = (dim.ah, dim.astride, 4)
 shared = multigpu.SharedFrame(rdr.out.shape(dim), rdr.out.dtype, rank, world, barrier=dist.barrier)
 reducer = multigpu.HistReducer(root=None)
+INTEGER = os.environ.get('INTEGER', '1') == '1'      # reduce unscaled integer level sums
 saved = {}
 
 
@@ -38,6 +39,7 @@ def hook(fb, dim_, stream):
     N.memcpy_htod(fb.d_seeds, mwc.make_seeds(fb.nstreams, host_seed=99), stream)
 
 
+hook.integer_sums = INTEGER
 rmgr.hist_hook = hook
 rmgr.band_filter = multigpu.BandFilter(rank, world, shared=shared)
 evt, out = rmgr.queue_frame(rdr, gnm, gprof, tc)
@@ -46,16 +48,18 @@ dist.barrier()
 if rank == 0:
     banded = np.array(shared.array)
     rmgr.band_filter = None
-    rmgr.hist_hook = lambda fb, dim_, stream: (
-        N.memcpy_htod(fb.d_front, saved['hist'], stream),
-        N.memcpy_htod(fb.d_seeds, mwc.make_seeds(fb.nstreams, host_seed=99), stream))
+    def inject(fb, dim_, stream):
+        N.memcpy_htod(fb.d_front, saved['hist'], stream)
+        N.memcpy_htod(fb.d_seeds, mwc.make_seeds(fb.nstreams, host_seed=99), stream)
+    inject.integer_sums = INTEGER
+    rmgr.hist_hook = inject
     evt, whole = rmgr.queue_frame(rdr, gnm, gprof, tc)
     evt.synchronize()
     whole = np.array(whole)
     print(json.dumps({'world': world, 'frame': [w, h, spp],
                       'output_rows': [multigpu.BandFilter(r, world, comm=False).output_rows(dim)
                                       for r in range(world)],
-                      'byte_identical': bool(np.array_equal(banded, whole)),
+                      'integer_sums': INTEGER, 'byte_identical': bool(np.array_equal(banded, whole)),
                       'differing_bytes': int((banded != whole).sum()),
                       'frame_mean': float(whole[..., :3].mean())}))
 dist.barrier()
