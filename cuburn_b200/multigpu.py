@@ -10,8 +10,13 @@ sharding are available in-process:
     the root with one NCCL reduce, and the root runs the filter chain.  With
     ``HistReducer(root=None)`` (all-reduce) + ``BandFilter`` the filter chain is
     sharded too: every GPU filters a band of rows plus the halo the chain's
-    stencils reach, and the bands are gathered on the root -- bit-identical to
-    filtering the whole frame on one GPU.
+    stencils reach -- bit-identical to filtering the whole frame on one GPU.
+    The bands are either gathered on the root (which converts and copies the
+    frame out alone) or, with ``BandFilter(shared=SharedFrame(...))``, each GPU
+    converts its own band and copies it over its own PCIe link into one
+    page-locked shared-memory host frame: no device exchange after the reduce.
+    ``HistReducer(integer_sums=True)`` reduces unscaled integer level sums, which
+    add up exactly in any order, so every rank holds the same bits.
   * animations: whole frames are independent (points are re-seeded every frame),
     so ``partition_frames`` deals frames round-robin and no collective is needed.
 
