@@ -671,5 +671,27 @@ class RenderManager(object):
         return self.copy_evt, h_out
 
 
+def frame_pipeline(rmgr, rdr, gnm, gprof, times, wait=None):
+    """
+    Render the frames at ``times`` one frame ahead of the host: frame k + 1 is queued
+    before frame k is waited for, so the device never idles while the host encodes or
+    writes (the loop of the reference's callers, main.py:62-76 and distribute.py:104-118,
+    as one generator).  Yields ``(n, evt, h_out)`` per finished frame in order, ``n``
+    counting from 1.  ``wait(evt)`` replaces the blocking ``evt.synchronize()`` (e.g. to
+    poll instead).
+    """
+    ahead = None
+    for n, tc in enumerate(list(times) + [None]):
+        queued = rmgr.queue_frame(rdr, gnm, gprof, tc) if tc is not None else None
+        if ahead is not None:
+            evt, h_out = ahead
+            if wait is not None:
+                wait(evt)
+            else:
+                evt.synchronize()
+            yield n, evt, h_out
+        ahead = queued
+
+
 def pk_width():
     return packer_mod.MAX_KNOTS

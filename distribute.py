@@ -116,16 +116,10 @@ def work(args, stdin=None, stdout=None):
             if getattr(filelike, 'close', None):
                 filelike.close()
 
-    pending = None
-    for idx, t in enumerate(list(times) + [None]):
-        nxt = rmgr.queue_frame(rdr, gnm, gprof, t) if t is not None else None
-        if pending is not None:
-            evt, buf = pending
-            evt.synchronize()
-            print('%30s: %s (%3d/%3d), %dms' % (addr, name, idx, len(times), evt.time()),
-                  file=sys.stderr, flush=True)
-            save(buf)
-        pending = nxt
+    for idx, evt, buf in render.frame_pipeline(rmgr, rdr, gnm, gprof, times):
+        print('%30s: %s (%3d/%3d), %dms' % (addr, name, idx, len(times), evt.time()),
+              file=sys.stderr, flush=True)
+        save(buf)
     write_str(stdout, CLOSING_ENCODER)
     save(None)
     write_str(stdout, DONE)

@@ -10,7 +10,6 @@ Accepts what the reference accepts: flam3 XML (.flam3 / .flame), cuburn JSON nod
 edges and animations, by file name or by ID inside a genome DB (-d).
 """
 import argparse
-import json
 import os
 import sys
 import time
@@ -18,6 +17,12 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from cuburn_b200 import profile  # noqa: E402
+
+# A frame that took longer than this is waited for by polling (the host thread sleeps
+# between polls instead of blocking inside the driver), as the reference does
+# (main.py:67-71).
+POLL_ABOVE_MS = 2000
+POLL_INTERVAL_S = 0.2
 
 
 def load_anim(args):
@@ -27,8 +32,46 @@ def load_anim(args):
         name = args.flame.split(':', 1)[1]
         return samples.GENOMES[name](), name
     from cuburn_b200.genome import db
-    gdb = db.connect(args.genomedb)
-    return gdb.get_anim(args.flame, args.half)
+    return db.connect(args.genomedb).get_anim(args.flame, args.half)
+
+
+def write_media(rdr, basename, frame):
+    """Encode one finished frame (``None``: flush the encoder) and write every file the
+    output module hands back as ``basename + suffix``; encoder logs go to stderr."""
+    media, logs = rdr.out.encode(frame)
+    for suffix, filelike in media.items():
+        with open(basename + suffix, 'wb') as fp:
+            fp.write(filelike.read())
+        close = getattr(filelike, 'close', None)
+        if close:
+            close()
+    for key, text in logs:
+        print('\n=== %s ===\n%s' % (key, text), file=sys.stderr)
+
+
+def write_preview(path, frame):
+    """--raw: the newest frame's raw buffer, replaced atomically (a viewer polls it)."""
+    try:
+        frame.tofile(path + '.tmp')
+        os.rename(path + '.tmp', path)
+    except Exception:
+        import traceback
+        print('Failed to write %s: %s' % (path, traceback.format_exc()), file=sys.stderr)
+
+
+class Waiter(object):
+    """How the host waits for a frame: block on its event while frames are quick, poll
+    once the previous frame took more than POLL_ABOVE_MS."""
+    def __init__(self):
+        self.last_ms = 0
+
+    def __call__(self, evt):
+        if self.last_ms > POLL_ABOVE_MS:
+            while not evt.query():
+                time.sleep(POLL_INTERVAL_S)
+        else:
+            evt.synchronize()
+        self.last_ms = evt.time()
 
 
 def main(args, prof):
@@ -38,53 +81,25 @@ def main(args, prof):
         sys.stdout.write(json_encode(gnm))
         return
     gprof = profile.wrap(prof, gnm)
-    frames = profile.enumerate_jobs(gprof, basename, args)
-    if not frames:
+    jobs = profile.enumerate_jobs(gprof, basename, args)
+    if not jobs:
         return
 
     from cuburn_b200 import _native, render
     _native.init(args.device or 0)
     rmgr = render.RenderManager()
     rdr = render.Renderer(gnm, gprof, keep=args.keep)
-    last_ms = 0
+    tag = '%d: ' % args.device if args.device is not None and args.device >= 0 else ''
+    wait = Waiter()
 
-    for name, times in frames:
-        def save(buf):
-            out, log = rdr.out.encode(buf)
-            for suffix, file_like in out.items():
-                with open(name + suffix, 'wb') as fp:
-                    fp.write(file_like.read())
-                if getattr(file_like, 'close', None):
-                    file_like.close()
-            for key, val in log:
-                print('\n=== %s ===\n%s' % (key, val), file=sys.stderr)
-
-        evt = buf = next_evt = next_buf = None
-        for idx, t in enumerate(list(times) + [None]):
-            evt, buf = next_evt, next_buf
-            if t is not None:
-                next_evt, next_buf = rmgr.queue_frame(rdr, gnm, gprof, t)
-            if not evt:
-                continue
-            if last_ms > 2000:
-                while not evt.query():
-                    time.sleep(0.2)
-            else:
-                evt.synchronize()
-            last_ms = evt.time()
-            save(buf)
+    for name, times in jobs:
+        for idx, evt, frame in render.frame_pipeline(rmgr, rdr, gnm, gprof, times, wait):
+            write_media(rdr, name, frame)
             if args.rawfn:
-                try:
-                    buf.tofile(args.rawfn + '.tmp')
-                    os.rename(args.rawfn + '.tmp', args.rawfn)
-                except Exception:
-                    import traceback
-                    print('Failed to write %s: %s' % (args.rawfn, traceback.format_exc()),
-                          file=sys.stderr)
-            print('%s%s (%3d/%3d), %dms' % (
-                ('%d: ' % args.device) if args.device is not None and args.device >= 0 else '',
-                name, idx, len(times), last_ms), file=sys.stderr)
-        save(None)
+                write_preview(args.rawfn, frame)
+            print('%s%s (%3d/%3d), %dms' % (tag, name, idx, len(times), wait.last_ms),
+                  file=sys.stderr)
+        write_media(rdr, name, None)
 
 
 def list_devices():
@@ -95,28 +110,36 @@ def list_devices():
             i, d['name'], d['cc'][0], d['cc'][1], d['sm_count'], d['total_mem'], d['l2_bytes']))
 
 
-if __name__ == '__main__':
+def build_parser():
+    """The reference's options (main.py:110-130) plus the profile options."""
     parser = argparse.ArgumentParser(description='Render fractal flames.')
-    parser.add_argument('flame', metavar='ID', type=str, nargs='?',
-                        help='Filename of the genome to render (or sample:NAME)')
-    parser.add_argument('-d', '--genomedb', metavar='PATH', type=str, default='.',
-                        help="Path to genome database (file or directory, default '.')")
-    parser.add_argument('--raw', metavar='PATH', type=str, dest='rawfn',
-                        help='Target file for raw buffer, to enable previews.')
-    parser.add_argument('--half', action='store_true',
-                        help='Use half-loops when converting nodes to animations')
-    parser.add_argument('--print', action='store_true',
-                        help='Print the animation and exit.')
-    parser.add_argument('--list-devices', action='store_true', help='List devices and exit.')
-    parser.add_argument('--device', metavar='NUM', type=int, help='GPU device number to use.')
-    parser.add_argument('--keep', action='store_true',
-                        help='Keep the generated source and cubin in $TMPDIR')
+    opt = parser.add_argument
+    opt('flame', metavar='ID', type=str, nargs='?',
+        help='Filename of the genome to render (or sample:NAME)')
+    opt('-d', '--genomedb', metavar='PATH', type=str, default='.',
+        help="Path to genome database (file or directory, default '.')")
+    opt('--raw', metavar='PATH', type=str, dest='rawfn',
+        help='Target file for raw buffer, to enable previews.')
+    opt('--half', action='store_true',
+        help='Use half-loops when converting nodes to animations')
+    opt('--print', action='store_true', help='Print the animation and exit.')
+    opt('--list-devices', action='store_true', help='List devices and exit.')
+    opt('--device', metavar='NUM', type=int, help='GPU device number to use.')
+    opt('--keep', action='store_true', help='Keep the generated source and cubin in $TMPDIR')
     profile.add_args(parser)
-    args = parser.parse_args()
+    return parser
+
+
+def run(argv=None):
+    parser = build_parser()
+    args = parser.parse_args(argv)
     if args.list_devices:
-        list_devices()
-    else:
-        if not args.flame:
-            parser.error('a flame is required')
-        pname, prof = profile.get_from_args(args)
-        main(args, prof)
+        return list_devices()
+    if not args.flame:
+        parser.error('a flame is required')
+    pname, prof = profile.get_from_args(args)
+    main(args, prof)
+
+
+if __name__ == '__main__':
+    run()
