@@ -115,6 +115,28 @@ def test_band_rows_cover_the_grid_with_equal_bands():
             assert bands[0][0] == 0 and bands[-1][1] == ah
 
 
+def test_output_rows_assemble_the_whole_frame(built):
+    """BandFilter.output_rows: the rows each GPU converts and copies into the shared host
+    frame cover every output row, and a rank only writes rows its own band produced
+    (rows written by two ranks -- overlapping bands -- hold identical bytes)."""
+    from cuburn_b200 import _native as N, multigpu
+    for w, h in ((640, 360), (1920, 1080), (3840, 2160), (7680, 4320), (320, 180), (64, 40),
+                 (100, 8), (33, 17)):
+        dim = N.calc_dim(w, h)
+        for world in (1, 2, 3, 4, 5, 7, 8):
+            writers = np.zeros(dim.h, int)
+            for r in range(world):
+                bf = multigpu.BandFilter(r, world, comm=False)
+                a, b = bf.output_rows(dim, 12)
+                assert 0 <= a <= b <= dim.h
+                row0, row1 = multigpu.band_rows(dim.ah, r, world)
+                lo = 0 if r == 0 else row0              # edge ranks also own the gutter rows
+                hi = dim.ah if r == world - 1 else row1
+                assert a == b or (lo <= a + 12 and b - 1 + 12 < hi), (w, h, world, r)
+                writers[a:b] += 1
+            assert writers.min() >= 1, (w, h, world)
+
+
 def test_c_abi_band_rows_match_the_host_mirror(built):
     import ctypes
     from cuburn_b200 import _native as N, multigpu
