@@ -555,7 +555,15 @@ def main():
                      'conversion' + (', NCCL all-reduce' if b.world > 1 else ''),
             'algorithmic_bytes_per_bin': 804,
             'achieved': 804.0 * nbins / (filt_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-            'frac': 804.0 * nbins / (filt_ms * 1e-3) / 1e9 / peak, 'ms': filt_ms}
+            'frac': 804.0 * nbins / (filt_ms * 1e-3) / 1e9 / peak, 'ms': filt_ms,
+            # not measured live: the ncu capture that says what the stage's dominant kernels
+            # are bound by (three quarters of the stage is the 8 x 31-tap bilateral passes)
+            'bilateral_main_pass': {
+                'bound': 'fma_pipe', 'frac': 0.61,
+                'source': 'profiles/r02_bilateral_kernels_ncu.md (ncu --set full, 1080p): '
+                          'sm__pipe_fma_cycles_active 60-61 %, XU pipe 45 %, issue 61 %, largest '
+                          'stall math-pipe throttle; DRAM 9-12 % of peak, bytes moved below the '
+                          'algorithmic 40 B/bin'}}
     if getattr(rmgr.band_filter, 'shared', None) is not None:
         rmgr.band_filter.shared.close()
     rmgr.fb.free()
