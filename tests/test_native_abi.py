@@ -118,6 +118,39 @@ def test_sample_genome_modules_use_vector_red(built, tmp_path):
     assert m and int(m.group(2)) <= 64 and int(m.group(4)) == 0 and int(m.group(1)) <= 32
 
 
+def test_every_module_variant_compiles(built, tmp_path):
+    """The iterate module exists in variants (still / motion blur) x (float4 / packed cells)
+    x (hot-bin cells) x (evict-last reductions) that RenderManager._iter picks per frame;
+    the rarely taken ones must build too -- here for a plain genome and for one with xaos
+    and opacity -- without local-memory arrays; register spill stays small under the
+    32-register cap (0 B for the plain genome; the xaos motion-blur variant, with its
+    per-previous-xform chains, spills 72 B)."""
+    import itertools
+    from cuburn_b200 import samples, render
+    xaos = samples.g3()
+    xaos['xforms']['0']['opacity'] = 0.35
+    xaos['xforms']['0']['chaos'] = {'0': 0.25, '1': 2.0}
+    xaos['xforms']['2']['chaos'] = {'1': 0.5, '2': 0.1}
+    seen = set()
+    for gnm in (samples.g3(), xaos):
+        for const, packed, hot, big in itertools.product((False, True), repeat=4):
+            if packed and hot:
+                continue                    # never combined (_hot_decision)
+            pk, src, mod = render.Renderer.compile(gnm, params_const=const, acc_packed=packed,
+                                                   hot_bins=hot, big_grid=big)
+            assert mod.cubin[:4] == b'\x7fELF'
+            seen.add(src)
+            p = tmp_path / 'variant.cubin'
+            p.write_bytes(mod.cubin)
+            usage = subprocess.run(['cuobjdump', '-res-usage', str(p)], stdout=subprocess.PIPE,
+                                   stderr=subprocess.STDOUT, text=True).stdout
+            m = re.search(r'Function cb_iter:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)',
+                          usage)
+            assert m and int(m.group(4)) == 0 and int(m.group(2)) <= 96, (const, packed, hot, big,
+                                                                         m and m.groups())
+    assert len(seen) == 24                  # every combination is its own source
+
+
 def test_compile_error_carries_log(built):
     from cuburn_b200 import _native as N
     with pytest.raises(N.CompileError) as e:
