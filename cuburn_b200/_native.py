@@ -7,6 +7,7 @@ raised (``NativeError``, or ``MemoryError`` for allocation failures, matching
 the reference's use of pycuda exceptions in render.py:140-147).
 """
 import ctypes
+import math
 import os
 from ctypes import (c_int, c_int32, c_uint32, c_uint64, c_size_t, c_float,
                     c_char_p, c_void_p, POINTER, byref)
@@ -391,7 +392,8 @@ class PinnedPool(object):
         if not isinstance(shape, (tuple, list)):
             shape = (shape,)
         shape = tuple(int(s) for s in shape)
-        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        used = math.prod(shape) * dtype.itemsize
+        nbytes = max(used, 1)
         bucket = self._free.setdefault(nbytes, [])
         if bucket:
             raw = bucket.pop()
@@ -402,7 +404,7 @@ class PinnedPool(object):
             self._all.append((raw, p.value))
         root = np.frombuffer(raw, dtype=np.uint8)
         weakref.finalize(root, bucket.append, raw)
-        return root[:int(np.prod(shape)) * dtype.itemsize].view(dtype).reshape(shape)
+        return root[:used].view(dtype).reshape(shape)
 
     def free_all(self):
         for raw, ptr in self._all:

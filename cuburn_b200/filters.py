@@ -17,11 +17,21 @@ from numpy import float32 as f32
 from . import _native as N
 
 
+_gauss_cache = {}
+
+
 def gauss_coefs(stdev=1):
-    """7-tap normalised Gaussian (set_blur_width, filters.py:11-16)."""
-    coefs = np.exp(np.float32(np.arange(-3, 4)) ** 2 / (-2 * stdev ** 2)).astype(np.float32)
-    coefs /= np.sum(coefs)
-    return (ctypes.c_float * 7)(*coefs.astype(np.float32))
+    """7-tap normalised Gaussian (set_blur_width, filters.py:11-16).  The returned ctypes
+    array is shared between calls with the same width (read-only by convention)."""
+    key = float(stdev)
+    out = _gauss_cache.get(key)
+    if out is None:
+        coefs = np.exp(np.float32(np.arange(-3, 4)) ** 2 / (-2 * stdev ** 2)).astype(np.float32)
+        coefs /= np.sum(coefs)
+        if len(_gauss_cache) > 256:         # an animated width: do not grow without bound
+            _gauss_cache.clear()
+        out = _gauss_cache[key] = (ctypes.c_float * 7)(*coefs.astype(np.float32))
+    return out
 
 
 # The first eight of the device's 16 filter directions (code/filters.py:8-17), for

@@ -26,15 +26,23 @@ class Wrapper(object):
         self._val, self.spec, self.path, self._params = val, spec, path, params
 
     # -- dispatch: spec node type -> wrap_<kind> --------------------------------------
-    _KINDS = ((Enum, 'enum'), (Spline, 'spline'), (Scalar, 'scalar'),
-              (RefScalar, 'refscalar'), (dict, 'dict'), (Map, 'Map'), (List, 'List'))
+    # (the hook names are the extension interface: subclasses override wrap_spline,
+    # wrap_refscalar, ... as in the reference, use.py:26-60)
+    _KINDS = ((Enum, 'wrap_enum'), (Spline, 'wrap_spline'), (Scalar, 'wrap_scalar'),
+              (RefScalar, 'wrap_refscalar'), (dict, 'wrap_dict'), (Map, 'wrap_Map'),
+              (List, 'wrap_List'))
+    _hook_of_type = {}          # exact spec type -> hook name, filled on first sight
 
     def wrap(self, name, spec, val):
-        path = self.path + (name,)
-        for kind, suffix in self._KINDS:
-            if isinstance(spec, kind):
-                return getattr(self, 'wrap_' + suffix)(path, spec, val)
-        return self.wrap_default(path, spec, val)
+        hook = self._hook_of_type.get(type(spec))
+        if hook is None:
+            hook = 'wrap_default'
+            for kind, method in self._KINDS:
+                if isinstance(spec, kind):
+                    hook = method
+                    break
+            self._hook_of_type[type(spec)] = hook
+        return getattr(self, hook)(self.path + (name,), spec, val)
 
     def wrap_default(self, path, spec, val):
         return val
@@ -132,11 +140,12 @@ class SplineEval(object):
     @staticmethod
     def normalize(knots, scale):
         if isinstance(knots, (int, float, np.number)):
-            v0 = v1 = 0.0
-            pts = [(0.0, float(knots)), (1.0, float(knots))]
-        elif len(knots) % 2 != 0:
+            # a constant: knots at 0 and 1, guard knots at -2 and 3, zero velocity
+            k = float(knots)
+            return np.array([[-2.0, 0.0, 1.0, 3.0], [k, k, k, k]])
+        if len(knots) % 2 != 0:
             raise ValueError('List with odd number of elements given')
-        elif len(knots) == 2:
+        if len(knots) == 2:
             v0 = v1 = 0.0
             pts = [(0.0, knots[0]), (1.0, knots[1])]
         else:
@@ -147,6 +156,8 @@ class SplineEval(object):
         v1 *= scale
         pts.sort()
 
+        # guard knots 2 time units outside [0, 1], placed so that the end tangents of the
+        # Catmull-Rom segments equal the stored velocities
         lead = 2.0
         if pts[0][0] >= 0:
             t1, p1_ = pts[1]
@@ -154,10 +165,7 @@ class SplineEval(object):
         if pts[-1][0] <= 1:
             t2, p2_ = pts[-2]
             pts.append((1 + lead, p2_ + (1 + lead - t2) * v1))
-
-        arr = np.zeros((2, len(pts)))
-        arr.T[:] = pts
-        return arr
+        return np.array(pts, dtype=np.float64).T.copy()
 
     def find_knots(self, itime):
         t_all = self.knots[0]
