@@ -196,6 +196,18 @@ class GenomePacker(object):
     def program_array(self):
         return np.asarray(self.program, dtype=np.int32).reshape(-1, PROG_WIDTH)
 
+    def _lookup(self, gnm, path):
+        """The genome's value at ``path``, or the schema default where a key is missing."""
+        attr = gnm
+        for name in path:
+            if isinstance(attr, dict) and name not in attr and name.isdigit() \
+                    and int(name) in attr:
+                name = int(name)            # chaos maps straight from the converter
+            if not isinstance(attr, dict) or name not in attr:
+                return resolve_spec(self.spec, path).default
+            attr = attr[name]
+        return attr
+
     def pack(self, gnm, times=None, knots=None):
         """
         Knot times and values for every row: two float32 [nrows][32] arrays
@@ -213,14 +225,11 @@ class GenomePacker(object):
         const_rows, const_vals = [], []
         for idx, path in enumerate(self.row_paths):
             attr = gnm
-            for name in path:
-                if isinstance(attr, dict) and name not in attr and name.isdigit() \
-                        and int(name) in attr:
-                    name = int(name)        # chaos maps straight from the converter
-                if not isinstance(attr, dict) or name not in attr:
-                    attr = resolve_spec(self.spec, path).default
-                    break
-                attr = attr[name]
+            try:
+                for name in path:           # the common case: every key is there
+                    attr = attr[name]
+            except (KeyError, TypeError, IndexError):
+                attr = self._lookup(gnm, path)
             if type(attr) in (int, float):
                 # a constant normalises to four equal knots at t = -2, 0, 1, 3; rows
                 # like this are most of a genome and are written in one go below
