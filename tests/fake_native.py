@@ -6,8 +6,9 @@ Everything that needs no device goes to the real library (cb_calc_dim, cb_band_r
 cb_convert_size, cb_sort_scratch_words, cb_last_error, NVRTC builds); every entry point that
 would touch a device is recorded as ``(name, args)`` and answers success without computing
 anything: allocations hand out addresses from a counter, pinned host memory is ordinary
-memory, events are always complete.  What is tested with it is WHICH calls the render
-manager issues, in which order and with which arguments -- never a pixel.
+memory, events are always complete and measure 1 ms per kernel launch issued between them.
+What is tested with it is WHICH calls the render manager issues, in which order and with
+which arguments -- never a pixel.
 """
 import ctypes
 import gc
@@ -49,6 +50,8 @@ class RecordingLib(object):
         self.device_sizes = {}          # address -> bytes
         self.d2h_hook = None            # f(dst_addr, src_addr, nbytes): fill host memory
         self.ctas_per_sm = 8
+        self._launched = 0              # kernel launches so far (the stand-in's clock)
+        self._event_at = {}             # event handle -> _launched when it was recorded
 
     # -- helpers for the tests -------------------------------------------------------------
     def names(self, start=0):
@@ -71,8 +74,11 @@ class RecordingLib(object):
             return getattr(self._real, name)
         handler = getattr(self, '_do_' + name[3:], None)
 
+        weight = KERNEL_CALLS.get(name, 0)
+
         def call(*args):
             self.calls.append((name, args))
+            self._launched += weight
             return handler(*args) if handler else 0
         return call
 
@@ -109,8 +115,13 @@ class RecordingLib(object):
     def _do_event_create(self, out):
         return self._handle(out)
 
+    def _do_event_record(self, evt, stream):
+        self._event_at[getattr(evt, 'value', evt)] = self._launched
+        return 0
+
     def _do_event_elapsed_ms(self, a, b, out):
-        _out(out).value = 1.0
+        at = self._event_at
+        _out(out).value = float(at[getattr(b, 'value', b)] - at[getattr(a, 'value', a)])
         return 0
 
     def _do_device_count(self, out):
