@@ -134,6 +134,25 @@ def test_frames_alternate_streams_and_wait_for_the_previous_conversion(lib):
     assert len(h2d) == 6
 
 
+def test_copy_false_reuses_the_uploaded_genome(lib):
+    """queue_frame(copy=False) (render.py:374,415-417): no packing, no H2D, and the
+    interpolation reads the device copy the previous call uploaded."""
+    from cuburn_b200 import samples, render
+    gnm = samples.g3()
+    gprof, tc = still_profile(gnm, 640, 360, 256)
+    rmgr = render.RenderManager(seed=5)
+    rdr = render.Renderer(gnm, gprof)
+    s0, _, _ = _frame(lib, rmgr, rdr, gnm, gprof, tc)
+    src0 = lib.args_of('cb_interp_rows', s0)[0][1:4]
+    s1, _, _ = _frame(lib, rmgr, rdr, gnm, gprof, tc, copy=False)
+    assert lib.args_of('cb_memcpy_h2d', s1) == []
+    assert lib.args_of('cb_interp_rows', s1)[0][1:4] == src0
+    assert lib.kernel_launches(s1) == 41
+    s2, _, _ = _frame(lib, rmgr, rdr, gnm, gprof, tc)           # copy=True: the other buffer
+    assert len(lib.args_of('cb_memcpy_h2d', s2)) == 6
+    assert lib.args_of('cb_interp_rows', s2)[0][1:4] != src0
+
+
 def test_motion_blur_stages_parameters_per_temporal_sample(lib):
     from cuburn_b200 import samples, render, profile
     gnm = samples.g6f(animated=True)
