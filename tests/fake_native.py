@@ -115,6 +115,9 @@ class RecordingLib(object):
     def _do_event_create(self, out):
         return self._handle(out)
 
+    def _do_comm_create(self, ident, rank, world, out):
+        return self._handle(out)
+
     def _do_event_record(self, evt, stream):
         self._event_at[getattr(evt, 'value', evt)] = self._launched
         return 0

@@ -329,6 +329,39 @@ def test_banded_still_filters_converts_and_copies_only_its_rows(lib, monkeypatch
                                            fb.d_right.ptr)
 
 
+def test_native_collectives_run_in_stream_order_around_the_filter_chain(lib):
+    """The library's own NCCL entry points (cb_comm.cu) as reducer and band gather: integer
+    sums out, cb_hist_reduce (all ranks), the 1/255 scale, the band's chain, cb_band_gather
+    to the root -- all on the frame's stream, no host synchronisation in between."""
+    from cuburn_b200 import samples, render, multigpu
+    gnm = samples.g6f()
+    w, h, spp = 1920, 1080, 400
+    gprof, tc = still_profile(gnm, w, h, spp)
+    rank, world = 1, 2
+    comm = multigpu.NativeComm(rank, world, exchange_id=lambda raw: raw)
+    assert lib.names().count('cb_comm_create') == 1 and 'cb_comm_unique_id' not in lib.names()
+    rmgr = render.RenderManager(seed=9, rank=rank, world=world)
+    rdr = render.Renderer(gnm, gprof)
+    rdr.hot = False
+    rmgr.hist_hook = multigpu.HistReducer(root=None, comm=comm, integer_sums=True)
+    rmgr.band_filter = multigpu.BandFilter(rank, world, root=0, comm=comm)
+    s, _, _ = _frame(lib, rmgr, rdr, gnm, gprof, tc)
+    names = [n for n in lib.names(s) if n in fake_native.KERNEL_CALLS or n.startswith(
+        ('cb_hist_reduce', 'cb_band_gather', 'cb_stream_sync', 'cb_device_sync'))]
+    assert names == INTERP + ['cb_fill32', 'cb_fill32', 'cb_iterate', 'cb_hist_finish',
+                              'cb_hist_reduce', 'cb_hist_finish'] + DEFAULT_CHAIN + \
+        ['cb_band_gather', 'cb_convert_rows']
+    red = lib.args_of('cb_hist_reduce', s)[0]
+    it = lib.iterations[-1]
+    assert red[0] is comm.handle and red[3] == -1 and red[4].value == it['stream']
+    gat = lib.args_of('cb_band_gather', s)[0]
+    assert gat[0] is comm.handle and gat[3] == 0 and gat[4].value == it['stream']
+    assert tuple(gat[2]._obj) == tuple(rmgr.fb.calc_dim(w, h))          # the whole frame's dims
+    assert rmgr.hist_hook.mean_reduce_ms() == 0.0                       # events bracket it
+    comm.close()
+    assert lib.names().count('cb_comm_destroy') == 1
+
+
 def test_frame_seed_reseeds_after_the_previous_conversion(lib):
     """queue_frame(frame_seed=k): a fresh seed table per frame (rank-specific when the
     frame's samples are split), uploaded once the previous frame no longer dithers from it."""
