@@ -137,6 +137,59 @@ def test_output_rows_assemble_the_whole_frame(built):
             assert writers.min() >= 1, (w, h, world)
 
 
+def test_shared_frame_is_one_segment_mapped_by_every_rank(built, monkeypatch):
+    """SharedFrame: rank 0 creates the POSIX shared-memory segment, the others open it by
+    name between two barriers, every rank page-locks its mapping (cb_host_register -- a
+    recording stand-in here) and the name is gone once all have it.  Two threads play the
+    ranks."""
+    import threading
+    import fake_native
+    from cuburn_b200 import multigpu
+    lib = fake_native.install(monkeypatch)
+    monkeypatch.setenv('MASTER_PORT', '29%03d' % (os.getpid() % 1000))
+    monkeypatch.setattr(multigpu.SharedFrame, '_seq', 0)
+    gate = threading.Barrier(2)
+    frames, errors = [None, None], []
+    expect = '/dev/shm/cuburn_b200_%s_1' % os.environ['MASTER_PORT']
+
+    def wait():
+        gate.wait(30)                   # a stuck rank fails the test instead of hanging it
+
+    def rank0():
+        try:
+            frames[0] = multigpu.SharedFrame((90, 160, 4), 'u1', 0, 2, barrier=wait)
+        except Exception as e:          # pragma: no cover
+            errors.append(e)
+            gate.abort()
+    t = threading.Thread(target=rank0, daemon=True)
+    t.start()
+    import time
+    for _ in range(1000):               # rank 0 creates and sizes the segment, then waits
+        if errors or (os.path.exists(expect) and os.path.getsize(expect) == 90 * 160 * 4):
+            break
+        time.sleep(0.01)
+    assert not errors and os.path.getsize(expect) == 90 * 160 * 4
+    multigpu.SharedFrame._seq = 0       # "another process": its own frame counter
+    frames[1] = multigpu.SharedFrame((90, 160, 4), 'u1', 1, 2, barrier=wait)
+    t.join(30)
+    assert not errors, errors
+    a, b = frames
+    assert a.path == b.path and not os.path.exists(a.path)      # unlinked, mappings live on
+    assert a.array.shape == b.array.shape == (90, 160, 4) and a.nbytes == 90 * 160 * 4
+    a.array[10:20] = 7                                           # rank 0's band ...
+    b.array[50:60] = 9
+    assert (b.array[10:20] == 7).all() and (a.array[50:60] == 9).all()     # ... seen by rank 1
+    reg = lib.args_of('cb_host_register')
+    assert sorted(x[1] for x in reg) == [a.nbytes, a.nbytes] and reg[0][0] != reg[1][0]
+    pa, pb = a.array.ctypes.data, b.array.ctypes.data
+    a.close()
+    b.close()
+    b.close()                                                    # idempotent
+    assert sorted(x[0] for x in lib.args_of('cb_host_unregister')) == sorted([pa, pb])
+    assert a.array is None
+    fake_native.uninstall()
+
+
 def test_c_abi_band_rows_match_the_host_mirror(built):
     import ctypes
     from cuburn_b200 import _native as N, multigpu

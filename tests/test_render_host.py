@@ -362,6 +362,37 @@ def test_native_collectives_run_in_stream_order_around_the_filter_chain(lib):
     assert lib.names().count('cb_comm_destroy') == 1
 
 
+def test_allocation_failure_frees_what_was_allocated_and_raises_memory_error(lib):
+    """render.py:133-147: if one of the four planes cannot be allocated the others are
+    released and MemoryError reaches the caller; a smaller frame then still renders."""
+    from cuburn_b200 import samples, render, _native as N
+    gnm = samples.g3()
+    rmgr = render.RenderManager(seed=5)
+    big = 16 * render.Framebuffers.calc_dim(7680, 4320).nbins
+    real_malloc, seen = lib._do_malloc, []
+
+    def malloc(nbytes, out):
+        if int(nbytes) == big:
+            seen.append(int(nbytes))
+            if len(seen) == 3:
+                return N.CB_ERR_NOMEM           # the third plane does not fit
+        return real_malloc(nbytes, out)
+    lib._do_malloc = malloc
+    gprof, tc = still_profile(gnm, 7680, 4320, 10)
+    rdr = render.Renderer(gnm, gprof)
+    s = lib.mark()
+    with pytest.raises(MemoryError):
+        rmgr.queue_frame(rdr, gnm, gprof, tc)
+    assert len(seen) == 3 and lib.names(s).count('cb_free') == 2
+    fb = rmgr.fb
+    assert fb.nbins is None and fb.d_front is fb.d_back is fb.d_left is fb.d_right is None
+    assert 'cb_iterate' not in lib.names(s)
+    gprof, tc = still_profile(gnm, 640, 360, 256)
+    rdr = render.Renderer(gnm, gprof)
+    s, _, out = _frame(lib, rmgr, rdr, gnm, gprof, tc)
+    assert out.shape == (360, 640, 4) and lib.kernel_launches(s) == 41
+
+
 def test_frame_seed_reseeds_after_the_previous_conversion(lib):
     """queue_frame(frame_seed=k): a fresh seed table per frame (rank-specific when the
     frame's samples are split), uploaded once the previous frame no longer dithers from it."""
