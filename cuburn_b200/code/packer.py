@@ -194,7 +194,14 @@ class GenomePacker(object):
 
     # ---- data ------------------------------------------------------------------
     def program_array(self):
-        return np.asarray(self.program, dtype=np.int32).reshape(-1, PROG_WIDTH)
+        """The precalc program as int32 [nops][PROG_WIDTH] (built once: the program is
+        complete when the constructor returns)."""
+        cached = getattr(self, '_program_array', None)
+        if cached is None or len(cached) != len(self.program):
+            cached = np.asarray(self.program, dtype=np.int32).reshape(-1, PROG_WIDTH)
+            cached.setflags(write=False)
+            self._program_array = cached
+        return cached
 
     def _lookup(self, gnm, path):
         """The genome's value at ``path``, or the schema default where a key is missing."""

@@ -317,28 +317,28 @@ class RenderManager(object):
             raise ValueError('genome needs %d rows / %d slots; limit is %d'
                              % (pk.nrows, pk.nslots, DevSrc.max_params))
         pool, s, src = self.fb.pool, self.stream_a, self.src_a
-        times = pool.allocate((pk.nrows, pk_width()), 'f4')
-        knots = pool.allocate((pk.nrows, pk_width()), 'f4')
-        pk.pack(gnm, times, knots)
-        N.memcpy_htod(src.d_times, times, s)
-        N.memcpy_htod(src.d_knots, knots, s)
-
         palsrc = dict((v[0], palette_decode(v[1:])) for v in gnm['palette'])
         if len(palsrc) > DevSrc.max_knots:
             raise ValueError('too many palettes')
         ptimes, pvals = zip(*sorted(palsrc.items()))
-        palettes = pool.allocate((len(palsrc), 256, 4), 'f4')
+        program = pk.program_array()
+        # one pinned staging block per frame, carved into the six arrays (64-byte aligned)
+        times, knots, palettes, palette_times, mag, prog = _carve(pool, (
+            ((pk.nrows, pk_width()), 'f4'), ((pk.nrows, pk_width()), 'f4'),
+            ((len(palsrc), 256, 4), 'f4'), ((DevSrc.max_knots,), 'f4'),
+            ((pk.nrows,), 'i4'), (program.shape, 'i4')))
+        pk.pack(gnm, times, knots)
+        N.memcpy_htod(src.d_times, times, s)
+        N.memcpy_htod(src.d_knots, knots, s)
+
         palettes[:] = pvals
-        palette_times = pool.allocate((DevSrc.max_knots,), 'f4')
         palette_times.fill(1e9)
         palette_times[:len(ptimes)] = ptimes
         N.memcpy_htod(src.d_pals, palettes, s)
         N.memcpy_htod(src.d_ptimes, palette_times, s)
 
-        mag = pool.allocate((pk.nrows,), 'i4')
         mag[:] = pk.row_mag
-        prog = pool.allocate(pk.program_array().shape, 'i4')
-        prog[:] = pk.program_array()
+        prog[:] = program
         N.memcpy_htod(src.d_row_mag, mag, s)
         N.memcpy_htod(src.d_program, prog, s)
         # keep the staging arrays of the last few frames alive: their async H2D copies
@@ -669,6 +669,20 @@ class RenderManager(object):
         self.info_a, self.info_b = self.info_b, self.info_a
         self.stream_a, self.stream_b = self.stream_b, self.stream_a
         return self.copy_evt, h_out
+
+
+def _carve(pool, specs):
+    """One pinned allocation from ``pool`` cut into arrays of the given (shape, dtype),
+    each starting on a 64-byte boundary; the block lives as long as any of them."""
+    import math
+    sizes = [math.prod(shape) * np.dtype(dt).itemsize for shape, dt in specs]
+    offsets, total = [], 0
+    for n in sizes:
+        offsets.append(total)
+        total += (n + 63) // 64 * 64
+    block = pool.allocate((max(total, 1),), 'u1')
+    return [block[off:off + n].view(dt).reshape(shape)
+            for off, n, (shape, dt) in zip(offsets, sizes, specs)]
 
 
 def frame_pipeline(rmgr, rdr, gnm, gprof, times, wait=None):

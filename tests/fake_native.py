@@ -99,9 +99,11 @@ class RecordingLib(object):
         return 0
 
     def _do_host_alloc(self, nbytes, out):
-        buf = ctypes.create_string_buffer(max(int(nbytes), 1))
-        addr = ctypes.addressof(buf)
-        self._host[addr] = buf
+        # page-aligned like cudaHostAlloc; _host: address -> (length, backing buffer)
+        n = max(int(nbytes), 1)
+        buf = ctypes.create_string_buffer(n + 4096)
+        addr = (ctypes.addressof(buf) + 4095) // 4096 * 4096
+        self._host[addr] = (n, buf)
         _out(out).value = addr
         return 0
 

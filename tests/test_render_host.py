@@ -132,6 +132,14 @@ def test_frames_alternate_streams_and_wait_for_the_previous_conversion(lib):
     # six pinned staging arrays per frame (knots, times, palettes, ...) and the output
     h2d = lib.args_of('cb_memcpy_h2d', s)
     assert len(h2d) == 6
+    # ... all of them in page-locked memory (an asynchronous copy from pageable memory would
+    # be staged synchronously by the driver), 64-byte aligned
+    pinned = [(a, a + n) for a, (n, _) in lib._host.items()]
+    for dst, src, nbytes, stream in h2d:
+        assert any(lo <= src.value and src.value + nbytes <= hi for lo, hi in pinned)
+        assert src.value % 64 == 0 and stream is not None
+    # ... and so is the frame handed back
+    assert any(lo <= out.ctypes.data < hi for lo, hi in pinned)
 
 
 def test_copy_false_reuses_the_uploaded_genome(lib):
